@@ -1,0 +1,82 @@
+"""In-tree nvcc build of libmpe_b200.so (sm_100a only).
+
+    python -m multiagent_rl_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the
+repo snapshot.  The fp64 env kernels are built with -fmad=false (validation build: every product and
+sum rounds like the float64 numpy reference).
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OBJ = os.path.join(HERE, 'csrc', 'build')
+LIB = os.path.join(HERE, 'libmpe_b200.so')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
+
+UNITS = [
+    ('env_kernels_f32.cu', []),
+    ('env_kernels_f64.cu', ['-fmad=false']),
+    ('actor_kernels.cu', []),
+    ('cabi.cu', ['-Xcompiler', '-fvisibility=default']),
+]
+
+
+def _sources():
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h')))
+    files = [os.path.join(CSRC, f) for f in files]
+    files.append(os.path.join(os.path.dirname(HERE), 'include', 'mpe_b200.h'))
+    files.append(os.path.abspath(__file__))
+    return files
+
+
+def source_hash():
+    h = hashlib.sha256()
+    for f in _sources():
+        with open(f, 'rb') as fp:
+            h.update(fp.read())
+    return h.hexdigest()
+
+
+def up_to_date():
+    stamp = LIB + '.hash'
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == source_hash()
+
+
+def _compile(unit):
+    src, extra = unit
+    obj = os.path.join(OBJ, src.replace('.cu', '.o'))
+    cmd = [NVCC] + ARCH + COMMON + extra + ['-c', os.path.join(CSRC, src), '-o', obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, ' '.join(cmd), r.stderr[-4000:]))
+    return obj
+
+
+def build(force=False, verbose=True):
+    if not force and up_to_date():
+        return LIB
+    if not os.path.exists(NVCC):
+        raise RuntimeError('nvcc not found at %s; libmpe_b200.so cannot be built' % NVCC)
+    os.makedirs(OBJ, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        objs = list(ex.map(_compile, UNITS))
+    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs + ['-lcudart_static', '-ldl', '-lrt', '-lpthread']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n%s' % r.stderr[-4000:])
+    with open(LIB + '.hash', 'w') as fp:
+        fp.write(source_hash())
+    if verbose:
+        print('built', LIB)
+    return LIB
+
+
+if __name__ == '__main__':
+    build(force='--force' in sys.argv)

@@ -1,0 +1,411 @@
+// extern "C" surface of libmpe_b200.so (declared in include/mpe_b200.h).  Handles, argument
+// checking, error text; all compute is in the kernel translation units behind env_launch.h /
+// actor_launch.h.  No host synchronisation except where the header says so.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/mpe_b200.h"
+#include "actor_launch.h"
+#include "env_launch.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char *where) {
+  g_err = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return MPE_ECUDA;
+}
+
+#define CK(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return fail_cuda(e_, #call);  \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+size_t real_size(int precision) { return precision == MPE_F64 ? sizeof(double) : sizeof(float); }
+
+}  // namespace
+
+struct MpeEnv {
+  mpe::EnvStateAny st;
+  int device = 0;
+  // lazily allocated device mirrors for the *_host entry points
+  int32_t *h_act_u = nullptr, *h_act_c = nullptr;
+  void *h_obs = nullptr, *h_rew = nullptr;
+  uint8_t *h_done = nullptr;
+};
+
+struct MpeActor {
+  mpe::ActorDev dev;
+  int device = 0;
+  float *h_obs = nullptr, *h_onehot = nullptr;  // device mirrors for actor_forward_host
+  int32_t *h_act_u = nullptr, *h_act_c = nullptr;
+  int64_t h_cap = 0;  // capacity in rows (B*N)
+};
+
+extern "C" {
+
+int mpe_abi_version(void) { return MPE_ABI_VERSION; }
+const char *mpe_last_error(void) { return g_err.c_str(); }
+
+int mpe_create(const MpeConfig *cfg, MpeEnv **out) {
+  if (cfg == nullptr || out == nullptr) return fail(MPE_EINVAL, "mpe_create: null argument");
+  *out = nullptr;
+  if (cfg->num_envs <= 0) return fail(MPE_EINVAL, "mpe_create: num_envs must be > 0");
+  if (cfg->precision != MPE_F32 && cfg->precision != MPE_F64) return fail(MPE_EINVAL, "mpe_create: bad precision");
+  int N = cfg->num_agents, L, D, dimc, act_c = 0;
+  switch (cfg->scenario) {
+    case MPE_SIMPLE_SPREAD:
+      if (N == 0) N = 3;
+      L = N; D = 4 + 2 * L; dimc = 2;
+      break;
+    case MPE_SIMPLE_REFERENCE:
+      if (N != 0 && N != 2) return fail(MPE_EUNSUPPORTED, "simple_reference has exactly 2 agents");
+      N = 2; L = 3; D = 21; dimc = 10; act_c = 10;
+      break;
+    case MPE_SIMPLE_SPEAKER_LISTENER:
+      if (N != 0 && N != 2) return fail(MPE_EUNSUPPORTED, "simple_speaker_listener has exactly 2 agents");
+      N = 2; L = 3; D = 11; dimc = 3;
+      break;
+    default:
+      return fail(MPE_EUNSUPPORTED, "mpe_create: unknown scenario");
+  }
+  if (!mpe::env_supported(cfg->scenario, N)) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "mpe_create: no kernel instantiated for scenario %d with %d agents", cfg->scenario, N);
+    return fail(MPE_EUNSUPPORTED, buf);
+  }
+  DeviceGuard g(cfg->device);
+  if (!g.ok) return fail(MPE_ECUDA, "mpe_create: cannot select device");
+  MpeEnv *env = new (std::nothrow) MpeEnv();
+  if (env == nullptr) return fail(MPE_EINVAL, "mpe_create: out of host memory");
+  env->device = cfg->device;
+  mpe::EnvStateAny &s = env->st;
+  s.B = cfg->num_envs; s.gid0 = cfg->env_id_offset; s.seed = cfg->seed;
+  s.max_speed = cfg->max_speed; s.accel = cfg->accel;
+  s.precision = cfg->precision; s.scenario = cfg->scenario;
+  s.N = N; s.L = L; s.D = D; s.dimc = dimc; s.act_u = 5; s.act_c = act_c;
+  s.max_episode_len = cfg->max_episode_len > 0 ? cfg->max_episode_len : 0;
+  const size_t rs = real_size(cfg->precision);
+  const size_t B = (size_t)s.B;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void **p, size_t bytes, int fill) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*p, fill, bytes);
+  };
+  alloc(&s.pv, (size_t)N * B * 4 * rs, 0);
+  alloc(&s.lm, (size_t)L * B * 2 * rs, 0);
+  alloc(&s.ep_ret, B * rs, 0);
+  alloc(reinterpret_cast<void **>(&s.goal), B * sizeof(int32_t), 0xFF);
+  alloc(reinterpret_cast<void **>(&s.episode), B * sizeof(uint32_t), 0xFF);  // first reset -> episode 0
+  alloc(reinterpret_cast<void **>(&s.tstep), B * sizeof(int32_t), 0);
+  alloc(reinterpret_cast<void **>(&s.stats), 4 * sizeof(double), 0);
+  if (cfg->scenario == MPE_SIMPLE_REFERENCE) alloc(&s.comm, (size_t)N * dimc * B * rs, 0);
+  if (e != cudaSuccess) {
+    mpe_destroy(env);
+    return fail_cuda(e, "mpe_create: cudaMalloc");
+  }
+  *out = env;
+  return MPE_OK;
+}
+
+int mpe_destroy(MpeEnv *env) {
+  if (env == nullptr) return MPE_OK;
+  DeviceGuard g(env->device);
+  cudaDeviceSynchronize();
+  mpe::EnvStateAny &s = env->st;
+  void *ptrs[] = {s.pv, s.lm, s.ep_ret, s.comm, s.goal, s.episode, s.tstep, s.stats,
+                  env->h_act_u, env->h_act_c, env->h_obs, env->h_rew, env->h_done};
+  for (void *p : ptrs)
+    if (p != nullptr) cudaFree(p);
+  delete env;
+  return MPE_OK;
+}
+
+int mpe_query(const MpeEnv *env, MpeDims *out) {
+  if (env == nullptr || out == nullptr) return fail(MPE_EINVAL, "mpe_query: null argument");
+  const mpe::EnvStateAny &s = env->st;
+  out->num_agents = s.N; out->num_landmarks = s.L; out->obs_dim = s.D; out->dim_c = s.dimc;
+  out->act_u = s.act_u; out->act_c = s.act_c; out->precision = s.precision; out->device = env->device;
+  out->num_envs = s.B; out->env_id_offset = s.gid0;
+  return MPE_OK;
+}
+
+int mpe_seed(MpeEnv *env, uint64_t seed) {
+  if (env == nullptr) return fail(MPE_EINVAL, "mpe_seed: null env");
+  DeviceGuard g(env->device);
+  env->st.seed = seed;
+  // restart the episode counters so that (seed, env id, episode) streams are reproducible
+  CK(cudaMemsetAsync(env->st.episode, 0xFF, (size_t)env->st.B * sizeof(uint32_t), 0));
+  return MPE_OK;
+}
+
+int mpe_reset(MpeEnv *env, const uint8_t *mask, void *obs_out, void *stream) {
+  if (env == nullptr) return fail(MPE_EINVAL, "mpe_reset: null env");
+  DeviceGuard g(env->device);
+  CK(mpe::launch_reset(env->st, mask, obs_out, static_cast<cudaStream_t>(stream)));
+  return MPE_OK;
+}
+
+int mpe_set_state(MpeEnv *env, const void *pos, const void *vel, const void *lm, const int32_t *goal, void *stream) {
+  if (env == nullptr) return fail(MPE_EINVAL, "mpe_set_state: null env");
+  DeviceGuard g(env->device);
+  CK(mpe::launch_set_state(env->st, pos, vel, lm, goal, static_cast<cudaStream_t>(stream)));
+  return MPE_OK;
+}
+
+int mpe_get_state(MpeEnv *env, void *pos, void *vel, void *lm, int32_t *goal, void *stream) {
+  if (env == nullptr) return fail(MPE_EINVAL, "mpe_get_state: null env");
+  DeviceGuard g(env->device);
+  CK(mpe::launch_get_state(env->st, pos, vel, lm, goal, static_cast<cudaStream_t>(stream)));
+  return MPE_OK;
+}
+
+int mpe_observe(MpeEnv *env, void *obs_out, void *stream) {
+  if (env == nullptr || obs_out == nullptr) return fail(MPE_EINVAL, "mpe_observe: null argument");
+  DeviceGuard g(env->device);
+  CK(mpe::launch_observe(env->st, obs_out, static_cast<cudaStream_t>(stream)));
+  return MPE_OK;
+}
+
+int mpe_step(MpeEnv *env, const int32_t *act_u, const int32_t *act_c, const void *comm_vec, void *obs, void *rew,
+             uint8_t *done, int32_t *info_i, void *info_f, void *stream) {
+  if (env == nullptr || act_u == nullptr) return fail(MPE_EINVAL, "mpe_step: null env or act_u");
+  if (env->st.scenario == MPE_SIMPLE_REFERENCE && act_c == nullptr && comm_vec == nullptr)
+    return fail(MPE_EINVAL, "mpe_step: simple_reference needs act_c or comm_vec");
+  DeviceGuard g(env->device);
+  CK(mpe::launch_step(env->st, act_u, act_c, comm_vec, obs, rew, done, info_i, info_f,
+                      static_cast<cudaStream_t>(stream)));
+  return MPE_OK;
+}
+
+int mpe_step_host(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_host, void *obs_host, void *rew_host,
+                  uint8_t *done_host, void *stream) {
+  if (env == nullptr || act_u_host == nullptr) return fail(MPE_EINVAL, "mpe_step_host: null env or act_u");
+  DeviceGuard g(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const mpe::EnvStateAny &s = env->st;
+  const size_t rows = (size_t)s.B * s.N, rs = real_size(s.precision);
+  if (env->h_act_u == nullptr) {
+    CK(cudaMalloc(&env->h_act_u, rows * sizeof(int32_t)));
+    CK(cudaMalloc(&env->h_act_c, rows * sizeof(int32_t)));
+    CK(cudaMalloc(&env->h_obs, rows * s.D * rs));
+    CK(cudaMalloc(&env->h_rew, rows * rs));
+    CK(cudaMalloc(&env->h_done, rows));
+  }
+  CK(cudaMemcpyAsync(env->h_act_u, act_u_host, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (act_c_host != nullptr)
+    CK(cudaMemcpyAsync(env->h_act_c, act_c_host, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  else if (s.scenario == MPE_SIMPLE_REFERENCE)
+    return fail(MPE_EINVAL, "mpe_step_host: simple_reference needs act_c");
+  CK(mpe::launch_step(s, env->h_act_u, act_c_host != nullptr ? env->h_act_c : nullptr, nullptr,
+                      obs_host != nullptr ? env->h_obs : nullptr, rew_host != nullptr ? env->h_rew : nullptr,
+                      done_host != nullptr ? env->h_done : nullptr, nullptr, nullptr, st));
+  if (obs_host != nullptr) CK(cudaMemcpyAsync(obs_host, env->h_obs, rows * s.D * rs, cudaMemcpyDeviceToHost, st));
+  if (rew_host != nullptr) CK(cudaMemcpyAsync(rew_host, env->h_rew, rows * rs, cudaMemcpyDeviceToHost, st));
+  if (done_host != nullptr) CK(cudaMemcpyAsync(done_host, env->h_done, rows, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MPE_OK;
+}
+
+int mpe_track_returns(MpeEnv *env, int32_t enable) {
+  if (env == nullptr) return fail(MPE_EINVAL, "mpe_track_returns: null env");
+  env->st.track = enable ? 1 : 0;
+  return MPE_OK;
+}
+
+int mpe_stats_read(MpeEnv *env, double out[4], int32_t clear, void *stream) {
+  if (env == nullptr || out == nullptr) return fail(MPE_EINVAL, "mpe_stats_read: null argument");
+  DeviceGuard g(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaMemcpyAsync(out, env->st.stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (clear) CK(cudaMemsetAsync(env->st.stats, 0, 4 * sizeof(double), st));
+  CK(cudaStreamSynchronize(st));
+  return MPE_OK;
+}
+
+int mpe_stats_ptr(MpeEnv *env, double **dev_ptr) {
+  if (env == nullptr || dev_ptr == nullptr) return fail(MPE_EINVAL, "mpe_stats_ptr: null argument");
+  *dev_ptr = env->st.stats;
+  return MPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// actor
+// ------------------------------------------------------------------------------------------------
+int actor_create(const ActorConfig *cfg, MpeActor **out) {
+  if (cfg == nullptr || out == nullptr) return fail(MPE_EINVAL, "actor_create: null argument");
+  *out = nullptr;
+  if (cfg->obs_dim <= 0 || cfg->obs_dim > mpe::kActorMaxD) return fail(MPE_EUNSUPPORTED, "actor_create: obs_dim out of range");
+  if (cfg->act0 <= 0 || cfg->act1 < 0 || cfg->act0 + cfg->act1 > mpe::kActorMaxA)
+    return fail(MPE_EUNSUPPORTED, "actor_create: head widths out of range");
+  DeviceGuard g(cfg->device);
+  if (!g.ok) return fail(MPE_ECUDA, "actor_create: cannot select device");
+  MpeActor *a = new (std::nothrow) MpeActor();
+  if (a == nullptr) return fail(MPE_EINVAL, "actor_create: out of host memory");
+  a->device = cfg->device;
+  mpe::actor_layout(cfg->obs_dim, cfg->act0, cfg->act1, cfg->has_model_head != 0, &a->dev);
+  cudaError_t e = cudaMalloc(&a->dev.blob, a->dev.blob_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(a->dev.blob, 0, a->dev.blob_floats * sizeof(float));
+  if (e != cudaSuccess) {
+    delete a;
+    return fail_cuda(e, "actor_create: cudaMalloc");
+  }
+  *out = a;
+  return MPE_OK;
+}
+
+int actor_destroy(MpeActor *a) {
+  if (a == nullptr) return MPE_OK;
+  DeviceGuard g(a->device);
+  cudaDeviceSynchronize();
+  void *ptrs[] = {a->dev.blob, a->h_obs, a->h_onehot, a->h_act_u, a->h_act_c};
+  for (void *p : ptrs)
+    if (p != nullptr) cudaFree(p);
+  delete a;
+  return MPE_OK;
+}
+
+int actor_load(MpeActor *a, const ActorWeights *w, void *stream) {
+  if (a == nullptr || w == nullptr) return fail(MPE_EINVAL, "actor_load: null argument");
+  if (!w->dense1_w || !w->dense1_b || !w->w_ih || !w->w_hh || !w->b_ih || !w->b_hh || !w->w_ih_r || !w->w_hh_r ||
+      !w->b_ih_r || !w->b_hh_r || !w->dense2_w || !w->dense2_b)
+    return fail(MPE_EINVAL, "actor_load: missing tensor");
+  if (a->dev.A1 > 0 && (!w->dense2b_w || !w->dense2b_b)) return fail(MPE_EINVAL, "actor_load: missing dense2_2");
+  if (a->dev.has_model && (!w->dense3_w || !w->dense3_b)) return fail(MPE_EINVAL, "actor_load: missing dense3");
+  DeviceGuard g(a->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float *host = nullptr;
+  CK(cudaMallocHost(&host, a->dev.blob_floats * sizeof(float)));
+  mpe::ActorHostWeights hw = {w->dense1_w, w->dense1_b, w->w_ih,     w->w_hh,     w->b_ih,      w->b_hh,
+                              w->w_ih_r,   w->w_hh_r,   w->b_ih_r,   w->b_hh_r,   w->dense2_w,  w->dense2_b,
+                              w->dense2b_w, w->dense2b_b, w->dense3_w, w->dense3_b};
+  mpe::actor_pack(a->dev, hw, host);
+  cudaError_t e = cudaMemcpyAsync(a->dev.blob, host, a->dev.blob_floats * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the pinned staging buffer is freed below
+  cudaFreeHost(host);
+  if (e != cudaSuccess) return fail_cuda(e, "actor_load: upload");
+  return MPE_OK;
+}
+
+int actor_forward(MpeActor *a, const float *obs, int64_t B, int32_t N, const float *gumbel, uint64_t seed,
+                  uint64_t step, int64_t env_id_offset, float *logits, float *next_state, int32_t *act_u,
+                  int32_t *act_c, float *onehot, void *stream) {
+  if (a == nullptr || obs == nullptr) return fail(MPE_EINVAL, "actor_forward: null argument");
+  if (B <= 0) return MPE_OK;
+  if (!mpe::actor_supported(N)) return fail(MPE_EUNSUPPORTED, "actor_forward: unsupported agent count");
+  if (next_state != nullptr && !a->dev.has_model) return fail(MPE_EINVAL, "actor_forward: no model head loaded");
+  DeviceGuard g(a->device);
+  mpe::ActorIO io;
+  io.obs = obs; io.gumbel = gumbel; io.logits = logits; io.next_state = next_state;
+  io.act_u = act_u; io.act_c = act_c; io.onehot = onehot;
+  io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
+  CK(mpe::launch_actor_forward(a->dev, io, static_cast<cudaStream_t>(stream)));
+  return MPE_OK;
+}
+
+int actor_forward_host(MpeActor *a, const float *obs_host, int64_t B, int32_t N, uint64_t seed, uint64_t step,
+                       int64_t env_id_offset, int32_t *act_u_host, int32_t *act_c_host, float *onehot_host,
+                       void *stream) {
+  if (a == nullptr || obs_host == nullptr) return fail(MPE_EINVAL, "actor_forward_host: null argument");
+  if (B <= 0) return MPE_OK;
+  if (!mpe::actor_supported(N)) return fail(MPE_EUNSUPPORTED, "actor_forward_host: unsupported agent count");
+  DeviceGuard g(a->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rows = B * N;
+  const int A = a->dev.A0 + a->dev.A1;
+  if (rows > a->h_cap) {
+    void *old[] = {a->h_obs, a->h_onehot, a->h_act_u, a->h_act_c};
+    for (void *p : old)
+      if (p != nullptr) cudaFree(p);
+    a->h_obs = a->h_onehot = nullptr; a->h_act_u = a->h_act_c = nullptr; a->h_cap = 0;
+    CK(cudaMalloc(&a->h_obs, (size_t)rows * a->dev.D * sizeof(float)));
+    CK(cudaMalloc(&a->h_onehot, (size_t)rows * A * sizeof(float)));
+    CK(cudaMalloc(&a->h_act_u, (size_t)rows * sizeof(int32_t)));
+    CK(cudaMalloc(&a->h_act_c, (size_t)rows * sizeof(int32_t)));
+    a->h_cap = rows;
+  }
+  CK(cudaMemcpyAsync(a->h_obs, obs_host, (size_t)rows * a->dev.D * sizeof(float), cudaMemcpyHostToDevice, st));
+  mpe::ActorIO io;
+  io.obs = a->h_obs; io.act_u = a->h_act_u; io.act_c = a->dev.A1 > 0 ? a->h_act_c : nullptr;
+  io.onehot = onehot_host != nullptr ? a->h_onehot : nullptr;
+  io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
+  CK(mpe::launch_actor_forward(a->dev, io, st));
+  if (act_u_host != nullptr) CK(cudaMemcpyAsync(act_u_host, a->h_act_u, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (act_c_host != nullptr && a->dev.A1 > 0)
+    CK(cudaMemcpyAsync(act_c_host, a->h_act_c, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (onehot_host != nullptr)
+    CK(cudaMemcpyAsync(onehot_host, a->h_onehot, (size_t)rows * A * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MPE_OK;
+}
+
+int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *obs_next, float *rew, int32_t *act_u,
+                int32_t *act_c, void *stream) {
+  if (env == nullptr || actor == nullptr) return fail(MPE_EINVAL, "mpe_rollout: null handle");
+  if (T <= 0) return MPE_OK;
+  if (env->st.precision != MPE_F32) return fail(MPE_EUNSUPPORTED, "mpe_rollout: fp32 envs only");
+  if (env->device != actor->device) return fail(MPE_EINVAL, "mpe_rollout: env and actor on different devices");
+  if (actor->dev.D != env->st.D) return fail(MPE_EINVAL, "mpe_rollout: actor obs_dim does not match the env");
+  if (actor->dev.A0 != 5 || actor->dev.A1 != env->st.act_c)
+    return fail(MPE_EINVAL, "mpe_rollout: actor heads do not match the env's action space");
+  if (!mpe::rollout_supported(env->st.scenario, env->st.N))
+    return fail(MPE_EUNSUPPORTED, "mpe_rollout: unsupported scenario / agent count");
+  DeviceGuard g(env->device);
+  mpe::RolloutIO io;
+  io.T = T; io.step0 = step0; io.obs_next = obs_next; io.rew = rew; io.act_u = act_u; io.act_c = act_c;
+  CK(mpe::launch_rollout(env->st, actor->dev, io, static_cast<cudaStream_t>(stream)));
+  return MPE_OK;
+}
+
+}  // extern "C"
+
+// precision dispatch for the env launchers declared in env_launch.h
+namespace mpe {
+bool env_supported(int scenario, int N) {
+  if (scenario == 0) return N == 2 || N == 3 || N == 4 || N == 6 || N == 9 || N == 12;
+  return (scenario == 1 || scenario == 2) && N == 2;
+}
+cudaError_t launch_reset(const EnvStateAny &a, const uint8_t *mask, void *obs, cudaStream_t st) {
+  return a.precision == MPE_F64 ? launch_reset_f64(a, mask, obs, st) : launch_reset_f32(a, mask, obs, st);
+}
+cudaError_t launch_observe(const EnvStateAny &a, void *obs, cudaStream_t st) {
+  return a.precision == MPE_F64 ? launch_observe_f64(a, obs, st) : launch_observe_f32(a, obs, st);
+}
+cudaError_t launch_step(const EnvStateAny &a, const int32_t *act_u, const int32_t *act_c, const void *comm_vec,
+                        void *obs, void *rew, uint8_t *done, int32_t *info_i, void *info_f, cudaStream_t st) {
+  return a.precision == MPE_F64 ? launch_step_f64(a, act_u, act_c, comm_vec, obs, rew, done, info_i, info_f, st)
+                                : launch_step_f32(a, act_u, act_c, comm_vec, obs, rew, done, info_i, info_f, st);
+}
+cudaError_t launch_set_state(const EnvStateAny &a, const void *pos, const void *vel, const void *lm,
+                             const int32_t *goal, cudaStream_t st) {
+  return a.precision == MPE_F64 ? launch_set_state_f64(a, pos, vel, lm, goal, st)
+                                : launch_set_state_f32(a, pos, vel, lm, goal, st);
+}
+cudaError_t launch_get_state(const EnvStateAny &a, void *pos, void *vel, void *lm, int32_t *goal, cudaStream_t st) {
+  return a.precision == MPE_F64 ? launch_get_state_f64(a, pos, vel, lm, goal, st)
+                                : launch_get_state_f32(a, pos, vel, lm, goal, st);
+}
+}  // namespace mpe

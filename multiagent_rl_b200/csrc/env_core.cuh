@@ -1,0 +1,322 @@
+// Per-env device logic of the particle world: reset, discrete action -> force, pairwise soft-contact
+// forces, damped integration, observation rows, rewards.  One thread owns one env and keeps every
+// entity in registers (all loops below are fully unrolled over the compile-time agent count).
+//
+// Reference rows (paths relative to the reference tree; the physics is in the `multiagent` package
+// imported at experiments/scenarios.py:2-3, so upstream function names are cited for those):
+//   _set_action        MultiAgentEnv._set_action       (called from experiments/run.py:44)
+//   physics()          World.step: apply_action_force, apply_environment_force /
+//                      get_collision_force, integrate_state
+//   obs_row()          experiments/scenarios.py:6-20, :23-42, :45-63
+//   reward()           Scenario.reward / benchmark_data of simple_spread, simple_reference,
+//                      simple_speaker_listener
+// The arithmetic is written in the reference's operation order so that the fp64 instantiation
+// (compiled with -fmad=false) differs from numpy only through exp/log1p rounding.
+#pragma once
+#include "common.cuh"
+
+namespace mpe {
+
+enum : int { kSpread = 0, kReference = 1, kSpeaker = 2 };
+
+template <int SC, int N_>
+struct Dims {
+  static constexpr int N = N_;
+  static constexpr int L = (SC == kSpread) ? N_ : 3;
+  static constexpr int D = (SC == kSpread) ? 4 + 2 * L : (SC == kReference ? 21 : 11);
+  static constexpr int DIMC = (SC == kSpread) ? 2 : (SC == kReference ? 10 : 3);
+  static constexpr int R = N * D;  // obs floats per env
+  static constexpr bool kCollide = (SC == kSpread);
+  static constexpr bool kHasGoal = (SC != kSpread);
+  static constexpr bool kTalks = (SC == kReference);  // comm visible in obs
+};
+
+// Device view of one shard's persistent state (structure-of-arrays over envs).
+template <typename T>
+struct EnvState {
+  T *pv;              // [N][B][4]  {px, py, vx, vy}   (16 B vector per agent per env in fp32)
+  T *lm;              // [L][B][2]  {x, y}
+  int32_t *goal;      // [B]  goal landmark of agent0 | agent1 << 8   (0xFF = None)
+  uint32_t *episode;  // [B]  episode index (Philox "t" of the reset stream)
+  int32_t *tstep;     // [B]  steps taken in the current episode
+  T *ep_ret;          // [B]  running episode return, summed over agents
+  T *comm;            // [N][DIMC][B] last message of every agent (simple_reference only, else NULL)
+  double *stats;      // [4]  sum(ret), sum(ret^2), n_episodes, n_steps
+  int64_t B;
+  int64_t gid0;       // global id of env 0
+  uint64_t seed;
+  T max_speed;        // < 0: None
+  T accel;            // < 0: None -> sensitivity 5.0
+  int32_t track;      // accumulate episode returns
+};
+
+template <typename T>
+__device__ __forceinline__ T softplus_pen(T dist, T dist_min) {
+  // np.logaddexp(0, -(dist - dist_min)/k) * k   with k = contact_margin
+  const T k = (T)1e-3;
+  const T y = -(dist - dist_min) / k;
+  T r;
+  if (y == (T)0) {
+    r = (T)0.693147180559945309417232121458176568;
+  } else {
+    const T tmp = -y;
+    if (tmp > (T)0)
+      r = log1p(exp(-tmp));
+    else if (tmp <= (T)0)
+      r = y + log1p(exp(tmp));
+    else
+      r = tmp;  // NaN
+  }
+  return r * k;
+}
+
+template <typename T>
+struct Underflow;  // (dist - dist_min) beyond which exp(-x/k) is exactly 0 in T, so the force is exactly 0
+template <>
+struct Underflow<float> {
+  static constexpr float v = 0.105f;
+};
+template <>
+struct Underflow<double> {
+  static constexpr double v = 0.75;
+};
+
+// Fold finished episodes of a warp into stats = {sum ret, sum ret^2, episodes, steps}.
+__device__ __forceinline__ void fold_stats(double *stats, double ret, double n_ep, double n_steps) {
+  double a = ret * n_ep, b = ret * ret * n_ep, c = n_ep, d = n_steps;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+  }
+  if ((threadIdx.x & 31) == 0 && c > 0.0) {
+    atomicAdd(stats + 0, a);
+    atomicAdd(stats + 1, b);
+    atomicAdd(stats + 2, c);
+    atomicAdd(stats + 3, d);
+  }
+}
+
+template <typename T, int SC, int N>
+struct Env {
+  using Dm = Dims<SC, N>;
+  static constexpr int L = Dm::L;
+  static constexpr int D = Dm::D;
+  T px[N], py[N], vx[N], vy[N];
+  T lx[L], ly[L];
+  int goal[2];  // landmark index or -1
+
+  __device__ __forceinline__ static T size_of_agent() {
+    return SC == kSpread ? (T)0.15 : (SC == kReference ? (T)0.05 : (T)0.075);
+  }
+  __device__ __forceinline__ static bool movable(int i) { return !(SC == kSpeaker && i == 0); }
+
+  __device__ __forceinline__ void load(const EnvState<T> &s, int64_t b) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const Vec4<T> v = ld4(s.pv + ((int64_t)i * s.B + b) * 4);
+      px[i] = v.x; py[i] = v.y; vx[i] = v.z; vy[i] = v.w;
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const Vec2<T> v = ld2(s.lm + ((int64_t)l * s.B + b) * 2);
+      lx[l] = v.x; ly[l] = v.y;
+    }
+    goal[0] = goal[1] = -1;
+    if (Dm::kHasGoal) {
+      const int32_t g = s.goal[b];
+      goal[0] = (g & 0xFF) == 0xFF ? -1 : (g & 0xFF);
+      goal[1] = ((g >> 8) & 0xFF) == 0xFF ? -1 : ((g >> 8) & 0xFF);
+    }
+  }
+
+  __device__ __forceinline__ void store_agents(const EnvState<T> &s, int64_t b) const {
+#pragma unroll
+    for (int i = 0; i < N; ++i) st4(s.pv + ((int64_t)i * s.B + b) * 4, Vec4<T>{px[i], py[i], vx[i], vy[i]});
+  }
+  __device__ __forceinline__ void store_world(const EnvState<T> &s, int64_t b) const {
+#pragma unroll
+    for (int l = 0; l < L; ++l) st2(s.lm + ((int64_t)l * s.B + b) * 2, Vec2<T>{lx[l], ly[l]});
+    if (Dm::kHasGoal) s.goal[b] = (goal[0] & 0xFF) | ((goal[1] & 0xFF) << 8);
+  }
+
+  // Scenario.reset_world: agents then landmarks ~ U[-1,1)^2, zero velocity, uniform goals.
+  __device__ __forceinline__ void reset(uint64_t seed, uint64_t gid, uint32_t episode) {
+    constexpr int E = N + L;
+#pragma unroll
+    for (int j = 0; j < (E + 1) / 2; ++j) {
+      const uint4 r = philox_raw(seed, gid, episode, kDomainReset, j);
+      set_entity_pos(2 * j, bits_to_pos<T>(r.x), bits_to_pos<T>(r.y));
+      if (2 * j + 1 < E) set_entity_pos(2 * j + 1, bits_to_pos<T>(r.z), bits_to_pos<T>(r.w));
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) vx[i] = vy[i] = (T)0;
+    goal[0] = goal[1] = -1;
+    if (Dm::kHasGoal) {
+      const uint4 r = philox_raw(seed, gid, episode, kDomainGoal, 0);
+      goal[0] = (int)__umulhi(r.x, (uint32_t)L);
+      if (SC == kReference) goal[1] = (int)__umulhi(r.y, (uint32_t)L);
+    }
+  }
+  __device__ __forceinline__ void set_entity_pos(int e, T x, T y) {
+    // e is a compile-time constant after unrolling
+    if (e < N) { px[e] = x; py[e] = y; }
+    else { lx[e - N] = x; ly[e - N] = y; }
+  }
+
+  // _set_action (one-hot branch) + World.step up to integrate_state.
+  __device__ __forceinline__ void physics(const int *act_u, T max_speed, T accel) {
+    const T sens = accel >= (T)0 ? accel : (T)5.0;
+    T fx[N], fy[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int a = act_u[i];
+      // u[0] += a[1] - a[2]; u[1] += a[3] - a[4]; u *= sensitivity
+      const T u0 = (T)0 + ((a == 1 ? (T)1 : (T)0) - (a == 2 ? (T)1 : (T)0));
+      const T u1 = (T)0 + ((a == 3 ? (T)1 : (T)0) - (a == 4 ? (T)1 : (T)0));
+      fx[i] = u0 * sens;
+      fy[i] = u1 * sens;
+    }
+    if (Dm::kCollide) {
+      const T dist_min = size_of_agent() + size_of_agent();
+      const T cut = dist_min + Underflow<T>::v;
+#pragma unroll
+      for (int a = 0; a < N; ++a) {
+#pragma unroll
+        for (int b = a + 1; b < N; ++b) {
+          const T dx = px[a] - px[b], dy = py[a] - py[b];
+          const T dist = sqrt(dx * dx + dy * dy);
+          if (!(dist > cut)) {  // beyond `cut` the penalty underflows to exactly 0 (NaN falls through)
+            const T pen = softplus_pen<T>(dist, dist_min);
+            const T gx = (T)100 * dx / dist * pen;
+            const T gy = (T)100 * dy / dist * pen;
+            fx[a] = gx + fx[a]; fy[a] = gy + fy[a];
+            fx[b] = -gx + fx[b]; fy[b] = -gy + fy[b];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (!movable(i)) continue;
+      T vxi = vx[i] * (T)0.75, vyi = vy[i] * (T)0.75;
+      vxi += fx[i] * (T)0.1;
+      vyi += fy[i] * (T)0.1;
+      if (max_speed >= (T)0) {
+        const T speed = sqrt(vxi * vxi + vyi * vyi);
+        if (speed > max_speed) {
+          vxi = vxi / speed * max_speed;
+          vyi = vyi / speed * max_speed;
+        }
+      }
+      vx[i] = vxi; vy[i] = vyi;
+      px[i] += vxi * (T)0.1;
+      py[i] += vyi * (T)0.1;
+    }
+  }
+
+  __device__ __forceinline__ static void goal_color(int g, T *c) {
+    const T hi = SC == kReference ? (T)0.75 : (T)0.65, lo = SC == kReference ? (T)0.25 : (T)0.15;
+    c[0] = g < 0 ? (T)0 : (g == 0 ? hi : lo);
+    c[1] = g < 0 ? (T)0 : (g == 1 ? hi : lo);
+    c[2] = g < 0 ? (T)0 : (g == 2 ? hi : lo);
+  }
+
+  // Observation of agent i -> row[0..D).  comm_other: message of the other agent (reference only).
+  template <typename Row>
+  __device__ __forceinline__ void obs_row(int i, Row row, const T *comm_other) const {
+    if (SC == kSpread) {
+      row[0] = vx[i]; row[1] = vy[i]; row[2] = px[i]; row[3] = py[i];
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        row[4 + 2 * l] = lx[l] - px[i];
+        row[5 + 2 * l] = ly[l] - py[i];
+      }
+    } else {
+      row[0] = vx[i]; row[1] = vy[i];
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        row[2 + 2 * l] = lx[l] - px[i];
+        row[3 + 2 * l] = ly[l] - py[i];
+      }
+      T c[3];
+      goal_color(goal[i], c);
+      row[8] = c[0]; row[9] = c[1]; row[10] = c[2];
+      if (SC == kReference) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) row[11 + k] = comm_other[k];
+      }
+    }
+  }
+
+  // Rewards (per agent, world.collaborative = False: experiments/scenarios.py:171) and the
+  // integer channels of simple_spread's benchmark_data.
+  __device__ __forceinline__ void reward(T *rew, int *coll, int &occupied, T &min_dists) const {
+    occupied = 0;
+    min_dists = (T)0;
+    if (SC == kSpread) {
+      T base = (T)0;
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        // min_a sqrt(d2) == sqrt(min_a d2): sqrt is monotone and correctly rounded
+        T m2 = (T)0;
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+          const T dx = px[a] - lx[l], dy = py[a] - ly[l];
+          const T d2 = dx * dx + dy * dy;
+          m2 = (a == 0) ? d2 : (d2 < m2 ? d2 : m2);
+        }
+        const T m = sqrt(m2);
+        base -= m;
+        min_dists += m;
+        occupied += (m < (T)0.1) ? 1 : 0;
+      }
+      const T dist_min = size_of_agent() + size_of_agent();
+      bool hit[N][N];
+#pragma unroll
+      for (int a = 0; a < N; ++a) {
+        {  // upstream also tests the agent against itself: dist 0 < dist_min, a constant -1 (NaN: no hit)
+          const T zx = px[a] - px[a], zy = py[a] - py[a];
+          hit[a][a] = sqrt(zx * zx + zy * zy) < dist_min;
+        }
+#pragma unroll
+        for (int b = a + 1; b < N; ++b) {
+          const T dx = px[a] - px[b], dy = py[a] - py[b];
+          const bool h = sqrt(dx * dx + dy * dy) < dist_min;
+          hit[a][b] = h; hit[b][a] = h;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        T r = base;
+        int c = 0;
+#pragma unroll
+        for (int a = 0; a < N; ++a)
+          if (hit[a][i]) { r -= (T)1; ++c; }
+        rew[i] = r;
+        coll[i] = c;
+      }
+    } else if (SC == kReference) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int g = goal[i];
+        const T gx = g == 0 ? lx[0] : (g == 1 ? lx[1] : lx[2]);
+        const T gy = g == 0 ? ly[0] : (g == 1 ? ly[1] : ly[2]);
+        const T dx = px[1 - i] - gx, dy = py[1 - i] - gy;
+        rew[i] = g < 0 ? (T)0 : -(dx * dx + dy * dy);
+        coll[i] = 0;
+      }
+    } else {
+      const int g = goal[0];
+      const T gx = g == 0 ? lx[0] : (g == 1 ? lx[1] : lx[2]);
+      const T gy = g == 0 ? ly[0] : (g == 1 ? ly[1] : ly[2]);
+      const T dx = px[1] - gx, dy = py[1] - gy;
+      rew[0] = rew[1] = -(dx * dx + dy * dy);
+      coll[0] = coll[1] = 0;
+    }
+  }
+};
+
+}  // namespace mpe

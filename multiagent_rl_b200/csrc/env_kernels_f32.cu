@@ -1,0 +1,23 @@
+// float instantiation of the env kernels.
+#include "env_kernels.cuh"
+
+namespace mpe {
+cudaError_t launch_reset_f32(const EnvStateAny &a, const uint8_t *mask, void *obs, cudaStream_t st) {
+  return launch_reset_t<float>(a, mask, obs, st);
+}
+cudaError_t launch_observe_f32(const EnvStateAny &a, void *obs, cudaStream_t st) {
+  return launch_observe_t<float>(a, obs, st);
+}
+cudaError_t launch_step_f32(const EnvStateAny &a, const int32_t *act_u, const int32_t *act_c, const void *comm_vec,
+                            void *obs, void *rew, uint8_t *done, int32_t *info_i, void *info_f, cudaStream_t st) {
+  return launch_step_t<float>(a, act_u, act_c, comm_vec, obs, rew, done, info_i, info_f, st);
+}
+cudaError_t launch_set_state_f32(const EnvStateAny &a, const void *pos, const void *vel, const void *lm,
+                                 const int32_t *goal, cudaStream_t st) {
+  return launch_set_state_t<float>(a, pos, vel, lm, goal, st);
+}
+cudaError_t launch_get_state_f32(const EnvStateAny &a, void *pos, void *vel, void *lm, int32_t *goal,
+                                 cudaStream_t st) {
+  return launch_get_state_t<float>(a, pos, vel, lm, goal, st);
+}
+}  // namespace mpe

@@ -1,0 +1,77 @@
+"""CPU checks of the drop-in boundary: the library loads, exports every symbol the header
+declares, and fails loudly (no fallback) without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from tests.conftest import ROOT
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, 'include', 'mpe_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    names = re.findall(r'^\s*(?:const\s+char\s*\*|int)\s*\*?\s*((?:mpe|actor)_\w+)\s*\(', src, flags=re.M)
+    return sorted(set(names))
+
+
+def test_library_is_built_in_tree():
+    from multiagent_rl_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), 'run python -m multiagent_rl_b200.build'
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    from multiagent_rl_b200 import _lib
+    declared = _header_functions()
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), 'libmpe_b200.so does not export %s' % name
+    assert sorted(_lib.SIGNATURES) == declared, 'python binding and header disagree'
+    assert _lib.load().mpe_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    from multiagent_rl_b200 import _lib
+    assert ctypes.sizeof(_lib.MpeConfig) == 64
+    assert ctypes.sizeof(_lib.MpeDims) == 48
+    assert ctypes.sizeof(_lib.ActorConfig) == 24
+    assert ctypes.sizeof(_lib.ActorWeights) == 16 * 8
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    from multiagent_rl_b200 import _lib
+    lib = _lib.load()
+    assert lib.mpe_create(None, None) == _lib.MPE_EINVAL
+    assert b'null' in lib.mpe_last_error()
+    h = ctypes.c_void_p()
+    cfg = _lib.MpeConfig(scenario=7, num_envs=4)
+    assert lib.mpe_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.MPE_EUNSUPPORTED
+    cfg = _lib.MpeConfig(scenario=0, num_agents=5, num_envs=4)
+    assert lib.mpe_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.MPE_EUNSUPPORTED
+    assert b'5 agents' in lib.mpe_last_error()
+    cfg = _lib.MpeConfig(scenario=0, num_envs=0)
+    assert lib.mpe_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.MPE_EINVAL
+    assert lib.mpe_step(None, None, None, None, None, None, None, None, None, None) == _lib.MPE_EINVAL
+    assert lib.mpe_destroy(None) == _lib.MPE_OK
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import multiagent_rl_b200 as m
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m.make_env('simple_spread')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m.FusedActor({})
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, 'multiagent_rl_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
