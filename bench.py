@@ -1,0 +1,367 @@
+"""bench.py - agent-steps/sec of the fused MPE step + observe + reward + actor path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs B_per_gpu] [--impl reference]
+
+One JSON line on stdout (rank 0).  Workload = BASELINE.json configs[1]: simple_spread, N = L = 3,
+65,536 env instances per GPU, one launch of the fused kernel (observe -> actor forward -> hard Gumbel
+sample -> World.step -> reward -> auto-reset every 25 steps) per "step"; weak scaling (per-GPU
+work fixed).  See DESIGN.md "Measurement" for how every field is derived.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCENARIO, N_AGENTS, OBS_DIM, ACT_DIM, EP_LEN = 'simple_spread', 3, 10, 5, 25
+SEED = 12345678  # main.py:41
+# algorithmic bytes of one env step: 41N + 8L + 4ND with N = L = 3, D = 10
+BYTES_PER_ENV_STEP = 41 * 3 + 8 * 3 + 4 * 3 * 10
+# algorithmic FLOPs of one actor forward per env: N (128 D + 49152 + 128 A)
+FLOPS_PER_ENV_STEP = N_AGENTS * (128 * OBS_DIM + 49152 + 128 * ACT_DIM)
+FP32_SIMT_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # FFMA peak at max clock (not a measured number)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--envs', type=int, default=65536, help='env instances per GPU')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline sample')
+    ap.add_argument('--no-extras', action='store_true', help='skip the env-only / 1M-env side measurements')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'],
+                'bf16_tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's loop body (experiments/run.py:36-65 without replay/optimize) on the oracle
+# --------------------------------------------------------------------------------------------------
+def cpu_loop(n_env_steps, seed, threads=1):
+    """Runs the reference-shaped rollout loop on the CPU oracle; returns (agent_steps, seconds)."""
+    import torch
+    import torch.nn.functional as F
+    from multiagent_rl_b200.networks import ActorNetwork
+    from oracle import mpe_ref
+    torch.set_num_threads(threads)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    env = mpe_ref.make_env(SCENARIO)
+    actor = ActorNetwork(OBS_DIM, ACT_DIM)
+    obs_n = env.reset()
+    episode_step = 0
+    t0 = time.perf_counter()
+    for _ in range(n_env_steps):
+        state = torch.from_numpy(np.array([np.stack(obs_n)], dtype='float32'))  # process_obs
+        with torch.no_grad():
+            logits = actor(state)
+        a = F.gumbel_softmax(logits.view(N_AGENTS, ACT_DIM), hard=True).view(1, N_AGENTS, ACT_DIM).numpy()
+        action_n_env = [np.array(x) for x in a[0].tolist()]
+        obs_n, rew_n, done_n, _ = env.step(action_n_env)
+        _ = np.sum(rew_n)
+        episode_step += 1
+        if all(done_n) or episode_step >= EP_LEN:
+            obs_n = env.reset()
+            episode_step = 0
+    return n_env_steps * N_AGENTS, time.perf_counter() - t0
+
+
+def _cpu_worker(args):
+    n, seed = args
+    return cpu_loop(n, seed, threads=1)
+
+
+def cpu_baseline(seconds):
+    """1 core, bounded sample of the same workload (rank 0, N = 1 only)."""
+    cpu_loop(100, SEED)  # warm-up
+    _, dt = cpu_loop(300, SEED)
+    n = max(500, int(300 * seconds / max(dt, 1e-6)))
+    steps, dt = cpu_loop(n, SEED)
+    return {'value': steps / dt, 'unit': 'agent-steps/s', 'cores': 1, 'kind': 'port',
+            'sample': '%d env steps (25-step episodes) of the float64 loop oracle + torch CPU actor + '
+                      'F.gumbel_softmax, 1 thread, %.1f s' % (n, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own (Python/numpy + torch CPU) implementation of the path,
+    restated in oracle/ because the physics package is not vendored, on all host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = 150  # env steps per process per bench step (bounded sample)
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_worker, [(20, SEED + i) for i in range(cores)])
+        t0 = time.perf_counter()
+        total = 0
+        for k in range(args.steps):
+            res = pool.map(_cpu_worker, [(per_step, SEED + k * cores + i) for i in range(cores)])
+            total += sum(r[0] for r in res)
+        dt = time.perf_counter() - t0
+    val = total / dt
+    line = {
+        'impl': 'reference', 'metric': 'agent-steps/sec', 'value': val, 'unit': 'agent-steps/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'simple_spread N=3 L=3 D=10 A=5, 25-step episodes, act+step loop '
+                               '(experiments/run.py:36-65), %d independent CPU processes x %d env steps per bench step'
+                               % (cores, per_step)},
+        'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d processes x %d steps x %d env steps' % (cores, args.steps, per_step)},
+        'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------------
+class Clocks(object):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) >= 8 and f[0] == str(self.index):
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[4:8]) if v.lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if vis:
+        try:
+            return int(vis.split(',')[local_rank])
+        except (ValueError, IndexError):
+            pass
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import multiagent_rl_b200 as m
+    from multiagent_rl_b200 import distributed as D
+    from oracle import actor_ref  # weights of the reference architecture, default-init distribution
+
+    rank, world, local = D.init_from_env()
+    if world != args.gpus:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch with torchrun)' % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    B = args.envs
+    off = rank * B
+    pk = peaks()
+
+    env = m.make_env(SCENARIO, num_envs=B, batched=True, seed=SEED, env_id_offset=off, max_episode_len=EP_LEN)
+    actor = m.FusedActor(actor_ref.init_state_dict(OBS_DIM, ACT_DIM, SEED), device=dev, seed=SEED)
+    env.reset()
+    # per-step outputs of the fused kernel (what a replay writer consumes)
+    obs_next = torch.empty((1, B, N_AGENTS, OBS_DIM), device=dev)
+    rew = torch.empty((1, B, N_AGENTS), device=dev)
+    act = torch.empty((1, B, N_AGENTS), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    from multiagent_rl_b200 import _lib
+    lib = _lib.load()
+
+    def fused_step(t):
+        _lib.check(lib.mpe_rollout(env._h, actor._h, 1, t, _lib.ptr(obs_next), _lib.ptr(rew), _lib.ptr(act), None,
+                                   _lib.current_stream(dev)), 'mpe_rollout')
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    t = 0
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        fused_step(t)
+        t += 1
+    clocks = Clocks(physical_gpu_index(local))
+    clocks.start()
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    for k in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+        ev[k][0].record()
+        fused_step(t)
+        launches += 1
+        t += 1
+        if world > 1 and t % EP_LEN == 0:  # the path's only collective: episode-return statistics
+            stats.copy_(torch.from_numpy(env.read_stats()))
+            dist.all_reduce(stats)
+        ev[k][1].record()
+    sync_all()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    ms = D.max_over_ranks(ms, device=dev)
+    clk = clocks.stop()
+    value = world * B * N_AGENTS * args.steps / (ms * 1e-3)
+    kernel_s = ms * 1e-3 / args.steps
+    tflops = B * FLOPS_PER_ENV_STEP / kernel_s / 1e12
+
+    # ---- e2e: the reference-facing host-buffer calls (get_exploration_action + env.step), pinned memory
+    e2e_steps = max(10, min(args.steps, 50))
+    h_obs = torch.empty((B, N_AGENTS, OBS_DIM), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((B, N_AGENTS), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((B, N_AGENTS), dtype=torch.uint8).pin_memory()
+    h_act = torch.empty((B, N_AGENTS), dtype=torch.int32).pin_memory()
+    h_obs.copy_(env.reset())
+    for _ in range(3):
+        actor.act_host(h_obs, step=t, env_id_offset=off, act_u=h_act)
+        env.step_host(h_act, out=(h_obs, h_rew, h_done))
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    for k in range(e2e_steps):
+        actor.act_host(h_obs, step=t + k, env_id_offset=off, act_u=h_act)  # H2D obs, kernel, D2H actions
+        env.step_host(h_act, out=(h_obs, h_rew, h_done))                  # H2D actions, kernel, D2H obs/rew/done
+        if (k + 1) % EP_LEN == 0:
+            h_obs.copy_(env.reset())
+    e1.record()
+    sync_all()
+    e2e_ms = D.max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3), device=dev)
+    rows = B * N_AGENTS
+    e2e = {'value': world * rows * e2e_steps / (e2e_ms * 1e-3), 'unit': 'agent-steps/s',
+           'h2d_bytes_per_step': rows * OBS_DIM * 4 + rows * 4,
+           'd2h_bytes_per_step': rows * 4 + rows * OBS_DIM * 4 + rows * 4 + rows,
+           'steps': e2e_steps, 'api': 'actor_forward_host + mpe_step_host (pinned host buffers)'}
+
+    extras = {}
+    if not args.no_extras:
+        extras = side_measurements(m, actor, dev, pk, off)
+
+    stats_now = D.reduce_return_stats(env.read_stats(), device=dev)
+    if rank != 0:
+        return
+    line = {
+        'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'simple_spread N=3 L=3 D=10 A=5, %d envs per GPU, fused observe+actor+sample+'
+                               'step+reward kernel (mpe_rollout T=1), in-kernel reset every 25 steps; per-step '
+                               'obs_next/rew/act written to HBM' % B,
+                   'envs_per_gpu': B, 'l2': 'flushed between timed iterations (256 MiB memset outside the events)',
+                   'actor_weights': 'random init, reference architecture (26,117 params)', 'seed': SEED},
+        'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': pk['bf16_tflops_sustained'],
+                     'unit': 'TFLOP/s', 'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': None,
+                     'kernel': 'k_rollout<simple_spread,3>', 'peak_source': pk['source'] + ' bf16 sustained',
+                     'note': 'actor GEMMs run as fp32 FFMA in this round (bit-parity path); against the fp32 SIMT '
+                             'peak of %.1f TFLOP/s the fraction is %.3f' % (FP32_SIMT_TFLOPS, tflops / FP32_SIMT_TFLOPS)},
+        'e2e': e2e, 'gpu_launches': launches, 'clocks': clk,
+        'episode_stats': {k: stats_now[k] for k in ('episodes', 'mean_return', 'std_return')},
+    }
+    line.update(extras)
+    if world == 1:
+        line['cpu_baseline'] = cpu_baseline(args.cpu_seconds)
+    print(json.dumps(line), flush=True)
+
+
+def side_measurements(m, actor, dev, pk, off):
+    """Env-only step kernel (the HBM-bound half of the path) at 1,048,576 envs, and the actor kernel alone."""
+    import torch
+    out = {}
+    B = 1 << 20
+    env = m.make_env(SCENARIO, num_envs=B, batched=True, seed=SEED, env_id_offset=off)
+    env.reset()
+    act = torch.randint(0, 5, (B, N_AGENTS), dtype=torch.int32, device=dev)
+    bufs = (torch.empty((B, N_AGENTS, OBS_DIM), device=dev), torch.empty((B, N_AGENTS), device=dev),
+            torch.empty((B, N_AGENTS), dtype=torch.uint8, device=dev))
+    for _ in range(5):
+        env.step(act, out=bufs)
+    torch.cuda.synchronize()
+    reps = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        env.step(act, out=bufs)  # 280 MB working set per launch > L2
+    e1.record()
+    torch.cuda.synchronize()
+    s = e0.elapsed_time(e1) * 1e-3 / reps
+    gbs = B * BYTES_PER_ENV_STEP / s / 1e9
+    out['roofline_env_step'] = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                                'frac': gbs / pk['hbm_gbs'], 'traffic': None, 'kernel': 'k_step<float,simple_spread,3>',
+                                'envs': B, 'agent_steps_per_s': B * N_AGENTS / s, 'us_per_launch': s * 1e6,
+                                'bytes_per_env_step': BYTES_PER_ENV_STEP, 'peak_source': pk['source']}
+    obs = bufs[0]
+    for _ in range(2):
+        actor.forward(obs[:262144])
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        actor.forward(obs[:262144])
+    e1.record()
+    torch.cuda.synchronize()
+    s = e0.elapsed_time(e1) * 1e-3 / 5
+    out['actor_forward_only'] = {'envs': 262144, 'agent_steps_per_s': 262144 * N_AGENTS / s,
+                                 'tflops': 262144 * FLOPS_PER_ENV_STEP / s / 1e12}
+    del env
+    return out
+
+
+def main():
+    args = parse()
+    if args.gpus > 1 and 'WORLD_SIZE' not in os.environ:
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', '29531', os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

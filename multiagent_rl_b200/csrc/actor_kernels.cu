@@ -469,13 +469,16 @@ __global__ void __launch_bounds__(kActorThreads, 1)
       // hand the tile's next-obs / rewards to the TMA engine (contiguous spans of the [B][N][.] outputs)
       const bool want_out = ro.obs_next != nullptr || ro.rew != nullptr;
       if (want_out) {
-        const bool tma_ok = ((reinterpret_cast<uintptr_t>(ro.obs_next) | reinterpret_cast<uintptr_t>(ro.rew)) & 15) == 0;
+        float *g_obs = ro.obs_next != nullptr ? ro.obs_next + (toff + env0) * R : nullptr;
+        float *g_rew = ro.rew != nullptr ? ro.rew + (toff + env0) * N : nullptr;
+        // TMA bulk stores need 16 B aligned destinations ([t][B] slices are not when B is odd)
+        const bool tma_ok = ((reinterpret_cast<uintptr_t>(g_obs) | reinterpret_cast<uintptr_t>(g_rew)) & 15) == 0;
         if (full && tma_ok) {
           if (tid < TB) fence_proxy_async_smem();
           __syncthreads();
           if (tid == 0) {
-            if (ro.obs_next != nullptr) bulk_store(ro.obs_next + (toff + env0) * R, sm.obs, TB * R * sizeof(float));
-            if (ro.rew != nullptr) bulk_store(ro.rew + (toff + env0) * N, sm.rew, TB * N * sizeof(float));
+            if (g_obs != nullptr) bulk_store(g_obs, sm.obs, TB * R * sizeof(float));
+            if (g_rew != nullptr) bulk_store(g_rew, sm.rew, TB * N * sizeof(float));
             bulk_commit();
             bulk_wait_read_all();
           }
