@@ -202,8 +202,11 @@ def test_list_surface_is_a_drop_in_for_the_reference_loop():
             assert done_n == ref_done and info_n == ref_info
             assert np.isfinite(np.sum(rew_n)) and all(done_n) is False
             episode_step += 1
-            if episode_step >= 25:
-                obs_n, ref_obs, episode_step = env.reset(), ref.reset(), 0
+            if episode_step >= 25:  # both sides draw from numpy's GLOBAL stream: replay the same state
+                st = np.random.get_state()
+                obs_n = env.reset()
+                np.random.set_state(st)
+                ref_obs, episode_step = ref.reset(), 0
 
 
 def test_benchmark_info_tuple():
