@@ -33,8 +33,8 @@ FP32_SIMT_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # FFMA peak at max clock (not
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--envs', type=int, default=65536, help='env instances per GPU')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline sample')
@@ -107,11 +107,14 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_step = 150  # env steps per process per bench step (bounded sample)
     ctx = mp.get_context('fork')
     with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
         for _ in range(max(args.warmup, 1)):
             pool.map(_cpu_worker, [(20, SEED + i) for i in range(cores)])
+        rate = 20 * max(args.warmup, 1) / (time.perf_counter() - t0)  # env steps / s / process
+        # bounded sample: env steps per process per bench step, sized so that K steps take <= ~90 s
+        per_step = int(max(5, min(150, rate * 90.0 / max(args.steps, 1))))
         t0 = time.perf_counter()
         total = 0
         for k in range(args.steps):
@@ -138,38 +141,57 @@ def run_reference(args):
 # clocks sampler
 # --------------------------------------------------------------------------------------------------
 class Clocks(object):
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """Samples SM clock and clock-event (throttle) reasons of one GPU through NVML from a thread,
+    every few ms, between start() and stop() - i.e. DURING the timed region."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
+               0x80: 'hw_power_brake_slowdown'}
 
-    def __init__(self, index):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    def __init__(self, index, period_s=0.004):
+        self.index, self.period = index, period_s
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thr = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001 - any NVML failure just leaves the record empty
+            self.err = repr(e)
+            return
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            f = [x.strip() for x in line.split(',')]
-            if len(f) >= 8 and f[0] == str(self.index):
-                self.rows.append(f)
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if r[2].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[4:8]) if v.lower().startswith('active')})
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(self.rows)}
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        out = {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.sm_max,
+               'reasons': sorted(self.reasons), 'samples': len(self.sm),
+               'power_w_max': max(self.power) if self.power else None, 'source': 'nvml, sampled inside the timed region'}
+        if self.err:
+            out['error'] = self.err
+        return out
 
 
 def physical_gpu_index(local_rank):

@@ -187,7 +187,8 @@ class BatchedMultiAgentEnv(object):
             if a.shape[0] != 5 + self.act_c:
                 raise AssertionError('action of agent %d has %d entries, expected %d' % (i, a.shape[0], 5 + self.act_c))
             d = int(np.argmax(a[:5]))
-            if self.force_discrete_action and a.dtype.kind == 'f':
+            movable = not (self.scenario_name == 'simple_speaker_listener' and i == 0)  # the speaker
+            if movable and self.force_discrete_action and a.dtype.kind == 'f':
                 a[:5] = 0.0  # in place, like upstream: the caller's arrays become exact one-hots
                 a[d] = 1.0
             act_u[0, i] = d

@@ -1,0 +1,46 @@
+"""Short, fixed workload for ncu captures (run under gpurun; see profiles/README.md):
+5 launches each of the env-only step kernel at 1,048,576 envs, the fused rollout kernel (T=1) at
+65,536 envs and the actor-forward kernel at 65,536 envs, simple_spread N=3, plus the N=6/12 steps."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import multiagent_rl_b200 as m  # noqa: E402
+from oracle import actor_ref  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+dev = torch.device('cuda:0')
+actor = m.FusedActor(actor_ref.init_state_dict(10, 5, 12345678), device=dev, seed=1)
+if which in ('all', 'step'):
+    B = 1 << 20
+    env = m.make_env('simple_spread', num_envs=B, batched=True, seed=1)
+    env.reset()
+    act = torch.randint(0, 5, (B, 3), dtype=torch.int32, device=dev)
+    out = (torch.empty((B, 3, 10), device=dev), torch.empty((B, 3), device=dev),
+           torch.empty((B, 3), dtype=torch.uint8, device=dev))
+    for _ in range(5):
+        env.step(act, out=out)
+    torch.cuda.synchronize()
+if which in ('all', 'rollout', 'actor'):
+    B = 65536
+    env = m.make_env('simple_spread', num_envs=B, batched=True, seed=1)
+    obs = env.reset()
+    if which != 'actor':
+        for _ in range(5):
+            env.rollout(actor, 1, record=True)
+    if which != 'rollout':
+        for _ in range(5):
+            actor.forward(obs)
+    torch.cuda.synchronize()
+if which in ('all', 'bign'):
+    for n, D in ((6, 16), (12, 28)):
+        B = 1 << 18
+        env = m.make_env('simple_spread', n=n, num_envs=B, batched=True, seed=1)
+        env.reset()
+        act = torch.randint(0, 5, (B, n), dtype=torch.int32, device=dev)
+        for _ in range(3):
+            env.step(act)
+        torch.cuda.synchronize()
+print('profile target done')
