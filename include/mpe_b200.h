@@ -139,6 +139,10 @@ int actor_destroy(MpeActor *actor);
 /* actor.load_state_dict(...) - rls/agent/multiagent/ddpg_gumbel_fix.py:231-241 */
 int actor_load(MpeActor *actor, const ActorWeights *w, void *stream);
 
+/* Implementation of the actor GEMMs: 0 = auto (tensor cores where supported), 1 = fp32 SIMT (FFMA),
+ * 2 = tcgen05 tensor cores with fp16 hi/lo split operands (fp32-level accuracy; 2-3 agents). */
+int actor_set_impl(MpeActor *actor, int32_t impl);
+
 /* Trainer.get_exploration_action - rls/agent/multiagent/ddpg_gumbel_fix.py:86-107:
  *   actor.forward (relu(dense1) -> BiLSTM over the agent axis -> relu -> dense2[_1,_2]) and
  *   F.gumbel_softmax(hard=True) == argmax(logits + G).

@@ -62,6 +62,7 @@ SIGNATURES = {
     'actor_create': (C.c_int, [C.POINTER(ActorConfig), C.POINTER(P)]),
     'actor_destroy': (C.c_int, [P]),
     'actor_load': (C.c_int, [P, C.POINTER(ActorWeights), P]),
+    'actor_set_impl': (C.c_int, [P, C.c_int32]),
     'actor_forward': (C.c_int, [P, P, C.c_int64, C.c_int32, P, C.c_uint64, C.c_uint64, C.c_int64, P, P, P, P, P, P]),
     'actor_forward_host': (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, P, P, P, P]),
     'mpe_rollout': (C.c_int, [P, P, C.c_int32, C.c_uint64, P, P, P, P, P]),

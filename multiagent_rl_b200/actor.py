@@ -33,7 +33,9 @@ class FusedActor(object):
     ``state_dict``: mapping with the reference's key names (torch tensors or numpy arrays).
     """
 
-    def __init__(self, state_dict, device=None, seed=0):
+    IMPLS = {'auto': 0, 'simt': 1, 'tc': 2}
+
+    def __init__(self, state_dict, device=None, seed=0, impl='auto'):
         if not torch.cuda.is_available():
             raise RuntimeError('multiagent_rl_b200 needs a CUDA device: the actor runs only as an sm_100a kernel')
         self._lib = _lib.load()
@@ -56,6 +58,7 @@ class FusedActor(object):
         h = C.c_void_p()
         _lib.check(self._lib.actor_create(C.byref(cfg), C.byref(h)), 'actor_create')
         self._h = h
+        self.set_impl(impl)
         self.load_state_dict(sd)
 
     def __del__(self):
@@ -63,6 +66,11 @@ class FusedActor(object):
         if h is not None and self._lib is not None:
             self._lib.actor_destroy(h)
             self._h = None
+
+    def set_impl(self, impl):
+        """'auto' (tensor cores where supported), 'simt' (fp32 FFMA) or 'tc' (tcgen05, fp16 hi/lo split)."""
+        _lib.check(self._lib.actor_set_impl(self._h, self.IMPLS[impl]), 'actor_set_impl')
+        self.impl = impl
 
     def load_state_dict(self, sd):
         """``actor.load_state_dict`` (rls/agent/multiagent/ddpg_gumbel_fix.py:231-241)."""

@@ -24,6 +24,7 @@ UNITS = [
     ('env_kernels_f32.cu', []),
     ('env_kernels_f64.cu', ['-fmad=false']),
     ('actor_kernels.cu', []),
+    ('tc_kernels.cu', []),
     ('cabi.cu', ['-Xcompiler', '-fvisibility=default']),
 ]
 

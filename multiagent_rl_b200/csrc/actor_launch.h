@@ -17,7 +17,20 @@ constexpr int kGateN = 128;     // i, f, g, o gates x 32 units
 // Device-resident packed weights.  Everything is stored k-major ("transposed") so that a thread's
 // output columns are contiguous:  Wg[dir][k][col'] with col' = ug*8 + gate*2 + uu holding the
 // reference row gate*32 + (ug + 16*uu) of [weight_ih | weight_hh]; biases b_ih + b_hh pre-summed.
+// fp16 hi/lo weight image of the tensor-core path (byte offsets; see tc_kernels.cu)
+struct TcDev {
+  unsigned char *blob = nullptr;
+  uint32_t bytes = 0;
+  int D = 0, Kx = 0, A0 = 0, A1 = 0, A = 0;
+  uint32_t off_wih[2][2] = {}, off_whh[2][2] = {}, off_w1[2] = {}, off_w2[2][2] = {};
+  uint32_t off_bg = 0, off_b1 = 0, off_b2 = 0;
+};
+
+enum { kImplAuto = 0, kImplSimt = 1, kImplTc = 2 };
+
 struct ActorDev {
+  TcDev tc;
+  int impl = kImplAuto;
   float *blob = nullptr;
   size_t blob_floats = 0;
   int D = 0, A0 = 0, A1 = 0, A = 0, Apad = 0, Dpad = 0, has_model = 0;
@@ -61,6 +74,12 @@ void actor_pack(const ActorDev &d, const ActorHostWeights &w, float *host_blob);
 bool actor_supported(int N);
 bool rollout_supported(int scenario, int N);
 cudaError_t launch_actor_forward(const ActorDev &w, const ActorIO &io, cudaStream_t st);
+// tensor-core path (tc_kernels.cu)
+void tc_layout(int D, int A0, int A1, TcDev *out);
+void tc_pack(const TcDev &t, const ActorHostWeights &w, unsigned char *host_image);
+bool tc_actor_supported(const TcDev &w, int N);
+cudaError_t launch_actor_forward_tc(const TcDev &w, const ActorIO &io, cudaStream_t st);
+cudaError_t launch_rollout_tc(const EnvStateAny &env, const TcDev &w, const RolloutIO &io, cudaStream_t st);
 cudaError_t launch_rollout(const EnvStateAny &env, const ActorDev &w, const RolloutIO &io, cudaStream_t st);
 
 }  // namespace mpe

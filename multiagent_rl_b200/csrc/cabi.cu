@@ -267,8 +267,11 @@ int actor_create(const ActorConfig *cfg, MpeActor **out) {
   if (a == nullptr) return fail(MPE_EINVAL, "actor_create: out of host memory");
   a->device = cfg->device;
   mpe::actor_layout(cfg->obs_dim, cfg->act0, cfg->act1, cfg->has_model_head != 0, &a->dev);
+  mpe::tc_layout(cfg->obs_dim, cfg->act0, cfg->act1, &a->dev.tc);
   cudaError_t e = cudaMalloc(&a->dev.blob, a->dev.blob_floats * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(a->dev.blob, 0, a->dev.blob_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&a->dev.tc.blob, a->dev.tc.bytes);
+  if (e == cudaSuccess) e = cudaMemset(a->dev.tc.blob, 0, a->dev.tc.bytes);
   if (e != cudaSuccess) {
     delete a;
     return fail_cuda(e, "actor_create: cudaMalloc");
@@ -281,7 +284,7 @@ int actor_destroy(MpeActor *a) {
   if (a == nullptr) return MPE_OK;
   DeviceGuard g(a->device);
   cudaDeviceSynchronize();
-  void *ptrs[] = {a->dev.blob, a->h_obs, a->h_onehot, a->h_act_u, a->h_act_c};
+  void *ptrs[] = {a->dev.blob, a->dev.tc.blob, a->h_obs, a->h_onehot, a->h_act_u, a->h_act_c};
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
   delete a;
@@ -306,7 +309,28 @@ int actor_load(MpeActor *a, const ActorWeights *w, void *stream) {
   cudaError_t e = cudaMemcpyAsync(a->dev.blob, host, a->dev.blob_floats * sizeof(float), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the pinned staging buffer is freed below
   cudaFreeHost(host);
+  if (e == cudaSuccess) {  // fp16 hi/lo image of the tensor-core path
+    unsigned char *img = nullptr;
+    e = cudaMallocHost(&img, a->dev.tc.bytes);
+    if (e == cudaSuccess) {
+      mpe::tc_pack(a->dev.tc, hw, img);
+      e = cudaMemcpyAsync(a->dev.tc.blob, img, a->dev.tc.bytes, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      cudaFreeHost(img);
+    }
+  }
   if (e != cudaSuccess) return fail_cuda(e, "actor_load: upload");
+  return MPE_OK;
+}
+
+static bool use_tc(const MpeActor *a, int N, bool needs_simt) {
+  if (a->dev.impl == mpe::kImplSimt || needs_simt) return false;
+  return mpe::tc_actor_supported(a->dev.tc, N);
+}
+
+int actor_set_impl(MpeActor *a, int32_t impl) {
+  if (a == nullptr || impl < 0 || impl > 2) return fail(MPE_EINVAL, "actor_set_impl: bad argument");
+  a->dev.impl = impl;
   return MPE_OK;
 }
 
@@ -322,7 +346,12 @@ int actor_forward(MpeActor *a, const float *obs, int64_t B, int32_t N, const flo
   io.obs = obs; io.gumbel = gumbel; io.logits = logits; io.next_state = next_state;
   io.act_u = act_u; io.act_c = act_c; io.onehot = onehot;
   io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
-  CK(mpe::launch_actor_forward(a->dev, io, static_cast<cudaStream_t>(stream)));
+  if (a->dev.impl == mpe::kImplTc && !use_tc(a, N, next_state != nullptr))
+    return fail(MPE_EUNSUPPORTED, "actor_forward: tensor-core path supports 2-3 agents, obs_dim <= 32, no model head");
+  if (use_tc(a, N, next_state != nullptr))
+    CK(mpe::launch_actor_forward_tc(a->dev.tc, io, static_cast<cudaStream_t>(stream)));
+  else
+    CK(mpe::launch_actor_forward(a->dev, io, static_cast<cudaStream_t>(stream)));
   return MPE_OK;
 }
 
@@ -352,7 +381,10 @@ int actor_forward_host(MpeActor *a, const float *obs_host, int64_t B, int32_t N,
   io.obs = a->h_obs; io.act_u = a->h_act_u; io.act_c = a->dev.A1 > 0 ? a->h_act_c : nullptr;
   io.onehot = onehot_host != nullptr ? a->h_onehot : nullptr;
   io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
-  CK(mpe::launch_actor_forward(a->dev, io, st));
+  if (use_tc(a, N, false))
+    CK(mpe::launch_actor_forward_tc(a->dev.tc, io, st));
+  else
+    CK(mpe::launch_actor_forward(a->dev, io, st));
   if (act_u_host != nullptr) CK(cudaMemcpyAsync(act_u_host, a->h_act_u, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (act_c_host != nullptr && a->dev.A1 > 0)
     CK(cudaMemcpyAsync(act_c_host, a->h_act_c, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -376,7 +408,10 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
   DeviceGuard g(env->device);
   mpe::RolloutIO io;
   io.T = T; io.step0 = step0; io.obs_next = obs_next; io.rew = rew; io.act_u = act_u; io.act_c = act_c;
-  CK(mpe::launch_rollout(env->st, actor->dev, io, static_cast<cudaStream_t>(stream)));
+  if (use_tc(actor, env->st.N, false))
+    CK(mpe::launch_rollout_tc(env->st, actor->dev.tc, io, static_cast<cudaStream_t>(stream)));
+  else
+    CK(mpe::launch_rollout(env->st, actor->dev, io, static_cast<cudaStream_t>(stream)));
   return MPE_OK;
 }
 
