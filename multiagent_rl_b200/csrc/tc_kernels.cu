@@ -22,6 +22,7 @@
 // the gate GEMM of the other direction.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "actor_launch.h"
@@ -143,6 +144,14 @@ __device__ __forceinline__ void mma3_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t
   }
 }
 
+// Optional phase timeline (MPE_TC_TIMELINE=1): clock64 stamps of the first tile of every CTA, read back with
+// the (undeclared, debug-only) export mpe_debug_tc_timeline.
+__device__ unsigned long long g_tc_timeline[148 * 96];
+#define TL(role, i)                                                                         \
+  do {                                                                                      \
+    if (dbg && first_tile && blockIdx.x < 148) g_tc_timeline[blockIdx.x * 96 + (role) * 32 + (i)] = clock64(); \
+  } while (0)
+
 struct TcSmem {
   unsigned char *w, *x, *h, *r;  // weight image; obs operands [N][hl][Kx/8][128][8]; h and relu(h) [dir][hl][4][128][8]
   float *stage_obs, *stage_rew;  // fp32 row staging for TMA loads/stores (aliases h / r, free outside the LSTM)
@@ -161,7 +170,7 @@ __host__ __device__ inline size_t tc_smem_bytes(uint32_t wbytes, int N, int Kx) 
 // ------------------------------------------------------------------------------------------------
 template <int SC, int N, bool FUSED>
 __global__ void __launch_bounds__(kTcThreads, 1)
-    k_tc(EnvState<float> s, TcDev w, ActorIO io, RolloutIO ro, int max_episode_len, int64_t ntiles) {
+    k_tc(EnvState<float> s, TcDev w, ActorIO io, RolloutIO ro, int max_episode_len, int64_t ntiles, int dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
   using Dm = Dims<SC, N>;
   const int D = FUSED ? Dm::D : w.D;
@@ -209,22 +218,27 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const uint32_t id_g = make_idesc_f16(128, 128), id_d1 = make_idesc_f16(128, 64), id_l = make_idesc_f16(128, 16);
       mbar_wait(&sm.bars[B_W], 0);
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const bool first_tile = tile == blockIdx.x;
         for (int it = 0; it < T; ++it) {
           mbar_wait(&sm.bars[B_X], ph_x); ph_x ^= 1;
           tc_fence_after();
+          TL(2, 0);
           for (int t = 0; t < N; ++t) {  // dense1: D1[t] = x[t] * W1^T
             const unsigned char *xh = sm.x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
             mma3_ss(tmem + t * 64, xh, xl, kChunkA, sm.w + w.off_w1[0], sm.w + w.off_w1[1], kHid * 16, Kx / 16, id_d1, false);
           }
           mma_commit(&sm.bars[B_D1]);
+          TL(2, 1);
           mbar_wait(&sm.bars[B_H1], ph_h1); ph_h1 ^= 1;
           tc_fence_after();
+          TL(2, 2);
           uint32_t seen = 0;
           for (int st = 0; st <= N; ++st) {
             for (int d = 0; d < 2; ++d) {
               if (st > 0) {  // h of step st-1 is in smem: its dense2 contribution, then (if any) the next gates
                 mbar_wait(&sm.bars[B_H0 + d], ph_h[d]); ph_h[d] ^= 1;
                 tc_fence_after();
+                TL(2, 3 + st * 4 + d * 2);
                 const int tp = d == 0 ? st - 1 : N - st;
                 const unsigned char *rh = sm.r + d * 16384, *rl = rh + 8192;
                 mma3_ss(tmem + col_l + tp * 16, rh, rl, kChunkA, sm.w + w.off_w2[d][0], sm.w + w.off_w2[d][1], 16 * 16, 2,
@@ -241,6 +255,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                           id_g, true);
                 }
                 mma_commit(&sm.bars[B_G0 + d]);
+                TL(2, 4 + st * 4 + d * 2);
               }
             }
           }
@@ -264,6 +279,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const int valid = (int)((nb - env0) < kRows ? (nb - env0) : kRows);
       const bool mine = row < valid;
       const int64_t b = env0 + row;
+      const bool first_tile = tile == blockIdx.x && row == 0;
+      TL(d, 0);
       if (!FUSED) {  // obs tile -> fp32 staging (TMA when whole and aligned)
         const float *src = io.obs + env0 * R;
         if (valid == kRows && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -319,10 +336,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         fence_proxy_async_smem();
         mbar_arrive(&sm.bars[B_X]);
+        TL(d, 1);
 
         // ---- dense1 epilogue: h1 = relu(D1/16 + b1) -> fp16 hi/lo A operand in TMEM ----
         mbar_wait(&sm.bars[B_D1], ph_d1); ph_d1 ^= 1;
         tc_fence_after();
+        TL(d, 2);
 #pragma unroll 1
         for (int t = 0; t < N; ++t) {
           uint32_t v[32];
@@ -345,6 +364,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&sm.bars[B_H1]);
+        TL(d, 3);
 
         // ---- LSTM cell math of this warpgroup's direction ----
         float c[kH];
@@ -355,6 +375,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int st = 0; st < N; ++st) {
           mbar_wait(&sm.bars[B_G0 + d], ph_g); ph_g ^= 1;
           tc_fence_after();
+          TL(d, 4 + 2 * st);
 #pragma unroll
           for (int ub = 0; ub < 4; ++ub) {  // 8 units x [i f g o] = 32 accumulator columns
             uint32_t v[32];
@@ -379,12 +400,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(&sm.bars[B_H0 + d]);
+          TL(d, 5 + 2 * st);
         }
 
         // ---- heads: logits -> Gumbel-max sample -> (fused) physics, reward, outputs ----
         if (d == 0) {
           mbar_wait(&sm.bars[B_L], ph_l); ph_l ^= 1;
           tc_fence_after();
+          TL(d, 12);
           int au[N], ac[N];
           const uint64_t step = FUSED ? ro.step0 + (uint64_t)it : io.step;
           const uint64_t seed = FUSED ? s.seed : io.seed;
@@ -425,6 +448,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (a >= w.A0 && a < w.A && z[a] > bcv) { bcv = z[a]; bc = a - w.A0; }
             }
             au[t] = bu; ac[t] = bc;
+            if (t == N - 1) TL(d, 15);
             sm.act[(row * N + t) * 2] = bu;
             sm.act[(row * N + t) * 2 + 1] = bc;
             if (!FUSED && mine && io.logits != nullptr) {
@@ -532,7 +556,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               }
           }
         }
+        TL(d, 13);
         bar_sync_n(1, 256);  // both warpgroups: the state / staging of this iteration is settled
+        TL(d, 14);
       }
     }
   }
@@ -560,7 +586,8 @@ static cudaError_t launch_tc_t(const EnvState<float> &s, const TcDev &w, const A
   const int64_t ntiles = (nenvs + kRows - 1) / kRows;
   const int nsm = sm_count_tc();
   const int grid = (int)(ntiles < nsm ? ntiles : nsm);
-  k_tc<SC, N, FUSED><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles);
+  static const int dbg = getenv("MPE_TC_TIMELINE") != nullptr;
+  k_tc<SC, N, FUSED><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles, dbg);
   return cudaGetLastError();
 }
 
@@ -591,3 +618,8 @@ cudaError_t launch_rollout_tc(const EnvStateAny &a, const TcDev &w, const Rollou
 }
 
 }  // namespace mpe
+
+// debug-only export (not part of include/mpe_b200.h)
+extern "C" __attribute__((visibility("default"))) int mpe_debug_tc_timeline(unsigned long long *out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, mpe::g_tc_timeline, sizeof(unsigned long long) * (size_t)n);
+}
