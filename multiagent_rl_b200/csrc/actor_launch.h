@@ -22,8 +22,8 @@ struct TcDev {
   unsigned char *blob = nullptr;
   uint32_t bytes = 0;
   int D = 0, Kx = 0, A0 = 0, A1 = 0, A = 0;
-  uint32_t off_wih[2][2] = {}, off_whh[2][2] = {}, off_w1[2] = {}, off_w2[2][2] = {};
-  uint32_t off_bg = 0, off_b1 = 0, off_b2 = 0;
+  uint32_t off_wih[2][2] = {}, off_whh[2][2] = {}, off_w1[2] = {};
+  uint32_t off_w2f = 0, off_bg = 0, off_b1 = 0, off_b2 = 0;
 };
 
 enum { kImplAuto = 0, kImplSimt = 1, kImplTc = 2 };

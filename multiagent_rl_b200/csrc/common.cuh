@@ -40,7 +40,9 @@ __device__ __forceinline__ T bits_to_pos(uint32_t r) {
 // Gumbel(0,1): u = ((r >> 9) + 0.5) * 2^-23 in (0,1), exact in fp32; g = -log(-log(u)).
 __device__ __forceinline__ float bits_to_gumbel(uint32_t r) {
   const float u = ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f;
-  return -logf(-logf(u));
+  // inner log accurate (the outer log turns its RELATIVE error into absolute error of g); the outer one
+  // only needs absolute accuracy (~5e-7), which the lg2.approx-based intrinsic gives for E in (6e-8, 17)
+  return -__logf(-logf(u));
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -31,9 +31,9 @@
 
 namespace mpe {
 
-constexpr int kTcThreads = 288;
+constexpr int kTcThreads = 320;
 constexpr int kRows = 128;
-constexpr float kWScale = 16.0f, kWInv = 0.0625f;
+constexpr float kWScale = 16.0f, kWInv = 0.0625f, kLog2e = 1.4426950408889634f;
 constexpr uint32_t kChunkA = kRows * 16;  // bytes of one K-chunk (8 halves) of a 128-row A operand
 
 // ------------------------------------------------------------------------------------------------
@@ -48,8 +48,7 @@ void tc_layout(int D, int A0, int A1, TcDev *o) {
   for (int d = 0; d < 2; ++d)
     for (int hl = 0; hl < 2; ++hl) { o->off_whh[d][hl] = off; off += kH * kGateN * 2; }
   for (int hl = 0; hl < 2; ++hl) { o->off_w1[hl] = off; off += (o->Kx > 0 ? o->Kx : 16) * kHid * 2; }
-  for (int d = 0; d < 2; ++d)
-    for (int hl = 0; hl < 2; ++hl) { o->off_w2[d][hl] = off; off += kH * 16 * 2; }
+  o->off_w2f = off; off += kHid * 16 * 4;  // dense2 heads, fp32 [k = dir*32 + unit][16]
   o->off_bg = off; off += 2 * kGateN * 4;
   o->off_b1 = off; off += kHid * 4;
   o->off_b2 = off; off += 16 * 4;
@@ -78,7 +77,7 @@ void tc_pack(const TcDev &t, const ActorHostWeights &w, unsigned char *img) {
         const int row = g * kH + u, n = u * 4 + g;  // packed gate column: unit-major, [i f g o] adjacent
         for (int k = 0; k < kHid; ++k) put_split(img, t.off_wih[d][0], t.off_wih[d][1], kGateN, n, k, wih[d][row * kHid + k]);
         for (int k = 0; k < kH; ++k) put_split(img, t.off_whh[d][0], t.off_whh[d][1], kGateN, n, k, whh[d][row * kH + k]);
-        bg[d * kGateN + n] = bih[d][row] + bhh[d][row];
+        bg[d * kGateN + n] = (bih[d][row] + bhh[d][row]) * (g == 2 ? -2.0f : -1.0f) * kLog2e;  // ex2 argument form
       }
   float *b1 = reinterpret_cast<float *>(img + t.off_b1), *b2 = reinterpret_cast<float *>(img + t.off_b2);
   for (int j = 0; j < kHid; ++j) {
@@ -87,8 +86,7 @@ void tc_pack(const TcDev &t, const ActorHostWeights &w, unsigned char *img) {
   }
   for (int a = 0; a < t.A; ++a) {
     const float *src = a < t.A0 ? w.dense2_w + a * kHid : w.dense2b_w + (a - t.A0) * kHid;
-    for (int d = 0; d < 2; ++d)
-      for (int u = 0; u < kH; ++u) put_split(img, t.off_w2[d][0], t.off_w2[d][1], 16, a, u, src[d * kH + u]);
+    for (int k = 0; k < kHid; ++k) reinterpret_cast<float *>(img + t.off_w2f)[k * 16 + a] = src[k];
     b2[a] = a < t.A0 ? w.dense2_b[a] : w.dense2b_b[a - t.A0];
   }
 }
@@ -96,8 +94,6 @@ void tc_pack(const TcDev &t, const ActorHostWeights &w, unsigned char *img) {
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_tc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_tc(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -144,31 +140,42 @@ __device__ __forceinline__ void mma3_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t
   }
 }
 
-// Optional phase timeline (MPE_TC_TIMELINE=1): clock64 stamps of the first tile of every CTA, read back with
-// the (undeclared, debug-only) export mpe_debug_tc_timeline.
-__device__ unsigned long long g_tc_timeline[148 * 96];
-#define TL(role, i)                                                                         \
-  do {                                                                                      \
-    if (dbg && first_tile && blockIdx.x < 148) g_tc_timeline[blockIdx.x * 96 + (role) * 32 + (i)] = clock64(); \
+// Optional phase timeline (MPE_TC_TIMELINE=1): clock64 stamps of the first tile of every warpgroup, read back
+// with the (undeclared, debug-only) export mpe_debug_tc_timeline.
+__device__ unsigned long long g_tc_timeline[148 * 128];
+#define TL(role, i)                                                                                              \
+  do {                                                                                                           \
+    if (dbg && first_tile && blockIdx.x < 148) g_tc_timeline[blockIdx.x * 128 + (role) * 32 + (i)] = clock64(); \
   } while (0)
 
-struct TcSmem {
-  unsigned char *w, *x, *h, *r;  // weight image; obs operands [N][hl][Kx/8][128][8]; h and relu(h) [dir][hl][4][128][8]
-  float *stage_obs, *stage_rew;  // fp32 row staging for TMA loads/stores (aliases h / r, free outside the LSTM)
-  int *act;                      // [128][N][2]
-  uint64_t *bars;                // see enum below
-  uint32_t *tmem_slot;
-};
-enum { B_W = 0, B_X, B_D1, B_H1, B_G0, B_G1, B_H0, B_H1R, B_L, B_OBS, B_COUNT };
+// barriers of one warpgroup's pipeline (indices into its own block of the barrier array)
+enum { B_X = 0, B_D1, B_H1, B_G, B_H, B_PER_WG };
 
+__host__ __device__ inline size_t tc_x_bytes(int N, int Kx) { return (size_t)N * 2 * (Kx / 8) * kChunkA; }
 __host__ __device__ inline size_t tc_smem_bytes(uint32_t wbytes, int N, int Kx) {
-  return (size_t)wbytes + (size_t)N * 2 * (Kx / 8) * kChunkA + 2 * 32768 + (size_t)kRows * N * 2 * 4 + B_COUNT * 8 + 64;
+  // weight image + per warpgroup: obs operands, recurrent h operand (hi/lo), action indices; + barriers
+  return (size_t)wbytes + 2 * (tc_x_bytes(N, Kx) + 16384 + (size_t)kRows * N * 2 * 4) + (1 + 2 * B_PER_WG) * 8 + 64;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(-x) with the exponent clamped so that products of two such terms stay finite
+__device__ __forceinline__ float exp_neg(float x) { return ex2_approx(fminf(-1.4426950408889634f * x, 57.0f)); }
+
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// the kernel: two independent tile pipelines per CTA (one per warpgroup), sharing the weight image
+//   warps 0-3 / 4-7 : warpgroup g = 0 / 1, thread r of the group owns env row r of the group's tile
+//   warps 8 / 9     : lane 0 issues every tcgen05.mma of warpgroup 0 / 1
+// TMEM columns of warpgroup g (base 256 g):  [0,128) gate accumulators of the current (direction, step)
+//                                            [128,192) dense1 accumulators of the next agent
+//                                            [192,256) h1 of the current agent as fp16 hi (32 cols) / lo (32 cols)
+// A warpgroup walks the 2N (direction, step) cells of its tile sequentially; while it waits for its gate GEMM
+// the other warpgroup's cell math fills the SM (the MUFU pipe is the shared bottleneck).
 // ------------------------------------------------------------------------------------------------
-template <int SC, int N, bool FUSED>
+template <int SC, int N, bool FUSED, int APAD>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_tc(EnvState<float> s, TcDev w, ActorIO io, RolloutIO ro, int max_episode_len, int64_t ntiles, int dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -177,153 +184,132 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int R = N * D;
   const int Kx = w.Kx;
   const int tid = threadIdx.x, warp = tid >> 5;
-  TcSmem sm;
-  sm.w = smem;
-  sm.x = smem + w.bytes;
-  sm.h = sm.x + (size_t)N * 2 * (Kx / 8) * kChunkA;
-  sm.r = sm.h + 32768;
-  sm.stage_obs = reinterpret_cast<float *>(sm.h);
-  sm.stage_rew = reinterpret_cast<float *>(sm.r);
-  sm.act = reinterpret_cast<int *>(sm.r + 32768);
-  sm.bars = reinterpret_cast<uint64_t *>(sm.act + kRows * N * 2);
-  sm.tmem_slot = reinterpret_cast<uint32_t *>(sm.bars + B_COUNT);
+  const size_t xb = tc_x_bytes(N, Kx);
+  const size_t wg_bytes = xb + 16384 + (size_t)kRows * N * 2 * 4;
+  unsigned char *sm_w = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + w.bytes + 2 * wg_bytes);  // [0] = weights, then 2 x B_PER_WG
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 1 + 2 * B_PER_WG);
 
   if (tid == 0) {
-    mbar_init(&sm.bars[B_W], 1);
-    mbar_init(&sm.bars[B_X], 256);
-    mbar_init(&sm.bars[B_D1], 1);
-    mbar_init(&sm.bars[B_H1], 256);
-    mbar_init(&sm.bars[B_G0], 1);
-    mbar_init(&sm.bars[B_G1], 1);
-    mbar_init(&sm.bars[B_H0], 128);
-    mbar_init(&sm.bars[B_H1R], 128);
-    mbar_init(&sm.bars[B_L], 1);
-    mbar_init(&sm.bars[B_OBS], 1);
+    mbar_init(&bars[0], 1);
+    for (int g = 0; g < 2; ++g) {
+      uint64_t *bb = bars + 1 + g * B_PER_WG;
+      mbar_init(&bb[B_X], 128);
+      mbar_init(&bb[B_D1], 1);
+      mbar_init(&bb[B_H1], 128);
+      mbar_init(&bb[B_G], 1);
+      mbar_init(&bb[B_H], 128);
+    }
     mbar_fence_init();
-    mbar_expect_tx(&sm.bars[B_W], w.bytes);
-    bulk_load(sm.w, w.blob, w.bytes, &sm.bars[B_W]);
+    mbar_expect_tx(&bars[0], w.bytes);
+    bulk_load(sm_w, w.blob, w.bytes, &bars[0]);
   }
-  if (warp == 8) tmem_alloc(sm.tmem_slot, 512);
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *sm.tmem_slot;
-  const uint32_t col_h1 = 256, col_l = 256 + 64 * N;
+  const uint32_t tmem_base = *tmem_slot;
   const int T = FUSED ? ro.T : 1;
+  const int g = warp >= 8 ? warp - 8 : (tid >> 7);  // pipeline index
+  unsigned char *sm_x = smem + w.bytes + g * wg_bytes;
+  unsigned char *sm_h = sm_x + xb;                  // [hl][4][128][8] halves
+  int *sm_act = reinterpret_cast<int *>(sm_h + 16384);
+  float *stage_obs = reinterpret_cast<float *>(sm_x);  // fp32 rows for the TMA store (x is dead by then)
+  float *stage_rew = stage_obs + kRows * R;
+  uint64_t *bb = bars + 1 + g * B_PER_WG;
+  const uint32_t tmem = tmem_base + g * 256;
+  const uint32_t col_d1 = 128, col_h1 = 192;
+  const int64_t tile0 = (int64_t)blockIdx.x * 2 + g, tile_stride = (int64_t)gridDim.x * 2;
 
-  if (warp == 8) {
-    // =============================== MMA issuer ===============================
+  if (warp >= 8) {
+    // =============================== MMA issuer of pipeline g ===============================
     if ((tid & 31) == 0) {
-      uint32_t ph_x = 0, ph_h1 = 0, ph_h[2] = {0, 0};
-      const uint32_t id_g = make_idesc_f16(128, 128), id_d1 = make_idesc_f16(128, 64), id_l = make_idesc_f16(128, 16);
-      mbar_wait(&sm.bars[B_W], 0);
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const bool first_tile = tile == blockIdx.x;
+      uint32_t ph_x = 0, ph_h1 = 0, ph_h = 0;
+      const uint32_t id_g = make_idesc_f16(128, 128), id_d1 = make_idesc_f16(128, 64);
+      mbar_wait(&bars[0], 0);
+      for (int64_t tile = tile0; tile < ntiles; tile += tile_stride) {
+        const bool first_tile = tile == tile0;
         for (int it = 0; it < T; ++it) {
-          mbar_wait(&sm.bars[B_X], ph_x); ph_x ^= 1;
+          mbar_wait(&bb[B_X], ph_x); ph_x ^= 1;
           tc_fence_after();
-          TL(2, 0);
-          for (int t = 0; t < N; ++t) {  // dense1: D1[t] = x[t] * W1^T
-            const unsigned char *xh = sm.x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
-            mma3_ss(tmem + t * 64, xh, xl, kChunkA, sm.w + w.off_w1[0], sm.w + w.off_w1[1], kHid * 16, Kx / 16, id_d1, false);
-          }
-          mma_commit(&sm.bars[B_D1]);
-          TL(2, 1);
-          mbar_wait(&sm.bars[B_H1], ph_h1); ph_h1 ^= 1;
-          tc_fence_after();
-          TL(2, 2);
-          uint32_t seen = 0;
-          for (int st = 0; st <= N; ++st) {
-            for (int d = 0; d < 2; ++d) {
-              if (st > 0) {  // h of step st-1 is in smem: its dense2 contribution, then (if any) the next gates
-                mbar_wait(&sm.bars[B_H0 + d], ph_h[d]); ph_h[d] ^= 1;
-                tc_fence_after();
-                TL(2, 3 + st * 4 + d * 2);
-                const int tp = d == 0 ? st - 1 : N - st;
-                const unsigned char *rh = sm.r + d * 16384, *rl = rh + 8192;
-                mma3_ss(tmem + col_l + tp * 16, rh, rl, kChunkA, sm.w + w.off_w2[d][0], sm.w + w.off_w2[d][1], 16 * 16, 2,
-                        id_l, (seen >> tp) & 1);
-                seen |= 1u << tp;
-              }
-              if (st < N) {
-                const int t = d == 0 ? st : N - 1 - st;
-                mma3_ts(tmem + d * 128, tmem + col_h1 + t * 64, tmem + col_h1 + t * 64 + 32, sm.w + w.off_wih[d][0],
-                        sm.w + w.off_wih[d][1], kGateN * 16, 4, id_g, false);
-                if (st > 0) {
-                  const unsigned char *hh = sm.h + d * 16384, *hl = hh + 8192;
-                  mma3_ss(tmem + d * 128, hh, hl, kChunkA, sm.w + w.off_whh[d][0], sm.w + w.off_whh[d][1], kGateN * 16, 2,
-                          id_g, true);
-                }
-                mma_commit(&sm.bars[B_G0 + d]);
-                TL(2, 4 + st * 4 + d * 2);
-              }
+          TL(2 + g, 0);
+          auto dense1 = [&](int t) {
+            const unsigned char *xh = sm_x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
+            mma3_ss(tmem + col_d1, xh, xl, kChunkA, sm_w + w.off_w1[0], sm_w + w.off_w1[1], kHid * 16, Kx / 16, id_d1, false);
+            mma_commit(&bb[B_D1]);
+          };
+          dense1(0);
+          for (int k = 0; k < 2 * N; ++k) {
+            const int d = k / N, st = k - d * N;
+            mbar_wait(&bb[B_H1], ph_h1); ph_h1 ^= 1;  // h1 of this cell's agent is in TMEM (and D1 is free again)
+            if (k > 0) { mbar_wait(&bb[B_H], ph_h); ph_h ^= 1; }  // previous cell done: G free, recurrent h in smem
+            tc_fence_after();
+            TL(2 + g, 1 + 2 * k);
+            mma3_ts(tmem, tmem + col_h1, tmem + col_h1 + 32, sm_w + w.off_wih[d][0], sm_w + w.off_wih[d][1], kGateN * 16, 4,
+                    id_g, false);
+            if (st > 0) mma3_ss(tmem, sm_h, sm_h + 8192, kChunkA, sm_w + w.off_whh[d][0], sm_w + w.off_whh[d][1], kGateN * 16, 2, id_g, true);
+            mma_commit(&bb[B_G]);
+            if (k + 1 < 2 * N) {  // dense1 of the next cell's agent runs behind the gates on the tensor pipe
+              const int d2 = (k + 1) / N, s2 = k + 1 - d2 * N;
+              dense1(d2 == 0 ? s2 : N - 1 - s2);
             }
+            TL(2 + g, 2 + 2 * k);
           }
-          mma_commit(&sm.bars[B_L]);
+          mbar_wait(&bb[B_H], ph_h); ph_h ^= 1;  // keep the phase in step with the last cell
         }
       }
     }
     __syncwarp();
   } else {
-    // =============================== epilogue warpgroups ===============================
-    const int d = tid >> 7, row = tid & 127;
+    // =============================== epilogue warpgroup g ===============================
+    const int row = tid & 127;
     const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
-    const float *bg = reinterpret_cast<const float *>(sm.w + w.off_bg) + d * kGateN;
-    const float *b1 = reinterpret_cast<const float *>(sm.w + w.off_b1);
-    const float *b2 = reinterpret_cast<const float *>(sm.w + w.off_b2);
-    uint32_t ph_d1 = 0, ph_g = 0, ph_l = 0, ph_obs = 0;
-    mbar_wait(&sm.bars[B_W], 0);  // biases are read from the weight image
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const float *b1 = reinterpret_cast<const float *>(sm_w + w.off_b1);
+    const float *b2 = reinterpret_cast<const float *>(sm_w + w.off_b2);
+    const float *w2f = reinterpret_cast<const float *>(sm_w + w.off_w2f);  // [64][16] fp32
+    uint32_t ph_d1 = 0, ph_g = 0;
+    mbar_wait(&bars[0], 0);  // biases / dense2 weights are read from the weight image
+    // De-phase the two pipelines: group 1 starts once group 0 is waiting for its first gate GEMM, so that one
+    // group's tensor-pipe wait is covered by the other group's cell math instead of both idling in lockstep.
+    bool staggered = false;
+    if (g == 1) bar_sync_n(3, 256);
+    else if (tile0 >= ntiles) { asm volatile("bar.arrive 3, 256;" ::: "memory"); staggered = true; }
+    for (int64_t tile = tile0; tile < ntiles; tile += tile_stride) {
       const int64_t env0 = tile * kRows;
       const int64_t nb = FUSED ? s.B : io.B;
       const int valid = (int)((nb - env0) < kRows ? (nb - env0) : kRows);
       const bool mine = row < valid;
       const int64_t b = env0 + row;
-      const bool first_tile = tile == blockIdx.x && row == 0;
-      TL(d, 0);
-      if (!FUSED) {  // obs tile -> fp32 staging (TMA when whole and aligned)
-        const float *src = io.obs + env0 * R;
-        if (valid == kRows && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-          if (tid == 0) {
-            mbar_expect_tx(&sm.bars[B_OBS], (uint32_t)(kRows * R * 4));
-            bulk_load(sm.stage_obs, src, (uint32_t)(kRows * R * 4), &sm.bars[B_OBS]);
-          }
-          mbar_wait(&sm.bars[B_OBS], ph_obs); ph_obs ^= 1;
-        } else {
-          for (int i = tid; i < kRows * R; i += 256) sm.stage_obs[i] = i < valid * R ? src[i] : 0.0f;
-          bar_sync_n(1, 256);
-        }
-      }
+      const bool first_tile = tile == tile0 && row == 0;
       for (int it = 0; it < T; ++it) {
-        // ---- observations -> fp16 hi/lo A operands (agents split between the warpgroups) ----
+        TL(g, 0);
+        // ---- observations -> fp16 hi/lo A operands ----
         {
           Env<float, SC, N> e;
           float comm[2][10];
-          if (FUSED) {
-            if (mine) {
-              e.load(s, b);
-              if (SC == kReference) {
+          if (FUSED && mine) {
+            e.load(s, b);
+            if (SC == kReference) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+              for (int i = 0; i < 2; ++i)
 #pragma unroll
-                  for (int k = 0; k < 10; ++k) comm[i][k] = s.comm[((int64_t)i * 10 + k) * s.B + b];
-              }
+                for (int k = 0; k < 10; ++k) comm[i][k] = s.comm[((int64_t)i * 10 + k) * s.B + b];
             }
           }
 #pragma unroll
           for (int t = 0; t < N; ++t) {
-            if ((t & 1) != d) continue;
             float xr[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) xr[k] = 0.0f;
             if (FUSED) {
               if (mine) e.obs_row(t, xr, SC == kReference ? comm[1 - (t & 1)] : nullptr);
-            } else {
+            } else if (mine) {
+              const float *src = io.obs + b * R + t * D;
 #pragma unroll
               for (int k = 0; k < 32; ++k)
-                if (k < D) xr[k] = sm.stage_obs[row * R + t * D + k];
+                if (k < D) xr[k] = src[k];
             }
-            unsigned char *xh = sm.x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
+            unsigned char *xh = sm_x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               if (c * 8 < Kx) {
@@ -335,236 +321,262 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&sm.bars[B_X]);
-        TL(d, 1);
+        mbar_arrive(&bb[B_X]);
+        TL(g, 1);
 
-        // ---- dense1 epilogue: h1 = relu(D1/16 + b1) -> fp16 hi/lo A operand in TMEM ----
-        mbar_wait(&sm.bars[B_D1], ph_d1); ph_d1 ^= 1;
-        tc_fence_after();
-        TL(d, 2);
-#pragma unroll 1
-        for (int t = 0; t < N; ++t) {
-          uint32_t v[32];
-          tmem_ld32(tmem + lane_base + t * 64 + d * 32, v);
-          tmem_wait_ld();
-          uint32_t hi[16], lo[16];
+        float lg[N][APAD];  // dense2 accumulators (both directions add into them)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a0 = fmaxf(fmaf(__uint_as_float(v[2 * j]), kWInv, b1[d * 32 + 2 * j]), 0.0f);
-            const float a1 = fmaxf(fmaf(__uint_as_float(v[2 * j + 1]), kWInv, b1[d * 32 + 2 * j + 1]), 0.0f);
-            __half h0, l0, h1, l1;
-            split_f16(a0, h0, l0);
-            split_f16(a1, h1, l1);
-            hi[j] = pack_h2(h0, h1);
-            lo[j] = pack_h2(l0, l1);
-          }
-          tmem_st16(tmem + lane_base + col_h1 + t * 64 + d * 16, hi);
-          tmem_st16(tmem + lane_base + col_h1 + t * 64 + 32 + d * 16, lo);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&sm.bars[B_H1]);
-        TL(d, 3);
+        for (int t = 0; t < N; ++t)
+#pragma unroll
+          for (int a = 0; a < APAD; ++a) lg[t][a] = b2[a];
 
-        // ---- LSTM cell math of this warpgroup's direction ----
-        float c[kH];
-#pragma unroll
-        for (int u = 0; u < kH; ++u) c[u] = 0.0f;
-        unsigned char *hh = sm.h + d * 16384, *hl = hh + 8192, *rh = sm.r + d * 16384, *rl = rh + 8192;
 #pragma unroll 1
-        for (int st = 0; st < N; ++st) {
-          mbar_wait(&sm.bars[B_G0 + d], ph_g); ph_g ^= 1;
-          tc_fence_after();
-          TL(d, 4 + 2 * st);
+        for (int d = 0; d < 2; ++d) {
+          const float *bg = reinterpret_cast<const float *>(sm_w + w.off_bg) + d * kGateN;
+          float c[kH];
 #pragma unroll
-          for (int ub = 0; ub < 4; ++ub) {  // 8 units x [i f g o] = 32 accumulator columns
-            uint32_t v[32];
-            tmem_ld32(tmem + lane_base + d * 128 + ub * 32, v);
-            tmem_wait_ld();
-            float hv[8], rv[8];
+          for (int u = 0; u < kH; ++u) c[u] = 0.0f;
+#pragma unroll 1
+          for (int st = 0; st < N; ++st) {
+            const int t = d == 0 ? st : N - 1 - st;
+            float pl[APAD];  // this cell's dense2 contribution, folded into lg[t] below
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = *reinterpret_cast<const float4 *>(bg + ub * 32 + j * 4);
-              const float ig = sigmoid_tc(fmaf(__uint_as_float(v[4 * j]), kWInv, bb.x));
-              const float fg = sigmoid_tc(fmaf(__uint_as_float(v[4 * j + 1]), kWInv, bb.y));
-              const float gg = tanh_tc(fmaf(__uint_as_float(v[4 * j + 2]), kWInv, bb.z));
-              const float og = sigmoid_tc(fmaf(__uint_as_float(v[4 * j + 3]), kWInv, bb.w));
-              const float cn = fmaf(fg, c[ub * 8 + j], ig * gg);
-              c[ub * 8 + j] = cn;
-              hv[j] = og * tanh_tc(cn);
-              rv[j] = fmaxf(hv[j], 0.0f);
+            for (int a = 0; a < APAD; ++a) pl[a] = 0.0f;
+            // ---- dense1 epilogue: h1 = relu(D1/16 + b1) -> fp16 hi/lo A operand in TMEM ----
+            mbar_wait(&bb[B_D1], ph_d1); ph_d1 ^= 1;
+            tc_fence_after();
+            TL(g, 2 + 4 * (d * N + st));
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t v[32];
+              tmem_ld32(tmem + lane_base + col_d1 + half * 32, v);
+              tmem_wait_ld();
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 bj = *reinterpret_cast<const float2 *>(b1 + half * 32 + 2 * j);
+                const float a0 = fmaxf(fmaf(__uint_as_float(v[2 * j]), kWInv, bj.x), 0.0f);
+                const float a1 = fmaxf(fmaf(__uint_as_float(v[2 * j + 1]), kWInv, bj.y), 0.0f);
+                __half h0, l0, h1, l1;
+                split_f16(a0, h0, l0);
+                split_f16(a1, h1, l1);
+                hi[j] = pack_h2(h0, h1);
+                lo[j] = pack_h2(l0, l1);
+              }
+              tmem_st16(tmem + lane_base + col_h1 + half * 16, hi);
+              tmem_st16(tmem + lane_base + col_h1 + 32 + half * 16, lo);
             }
-            store_chunk_split(hh + ub * kChunkA, hl + ub * kChunkA, row, hv);
-            store_chunk_split(rh + ub * kChunkA, rl + ub * kChunkA, row, rv);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bb[B_H1]);
+            if (g == 0 && !staggered) { asm volatile("bar.arrive 3, 256;" ::: "memory"); staggered = true; }
+            TL(g, 3 + 4 * (d * N + st));
+
+            // ---- LSTM cell math on the gate accumulators ----
+            mbar_wait(&bb[B_G], ph_g); ph_g ^= 1;
+            tc_fence_after();
+            TL(g, 4 + 4 * (d * N + st));
+#pragma unroll
+            for (int ub = 0; ub < 4; ++ub) {  // 8 units x [i f g o] = 32 accumulator columns
+              uint32_t v[32];
+              tmem_ld32(tmem + lane_base + ub * 32, v);
+              tmem_wait_ld();
+              float hv[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                // biases are stored pre-multiplied by -log2(e) (x2 for the g gate): one FFMA yields the ex2 argument
+                const float4 bbv = *reinterpret_cast<const float4 *>(bg + ub * 32 + j * 4);
+                const float ei = ex2_approx(fmaf(__uint_as_float(v[4 * j]), -kWInv * kLog2e, bbv.x));
+                const float ef = ex2_approx(fmaf(__uint_as_float(v[4 * j + 1]), -kWInv * kLog2e, bbv.y));
+                const float eg = ex2_approx(fminf(fmaf(__uint_as_float(v[4 * j + 2]), -2.0f * kWInv * kLog2e, bbv.z), 57.0f));
+                const float eo = ex2_approx(fmaf(__uint_as_float(v[4 * j + 3]), -kWInv * kLog2e, bbv.w));
+                // sigmoid(i) tanh(g) = (1 - eg) / ((1 + ei)(1 + eg)); sigmoid(f) = 1 / (1 + ef).  ei/ef/eo may
+                // overflow to +inf (quotient 0); eg/ec are clamped so that 1 - e stays finite.
+                const float ig = __fdividef(1.0f - eg, (1.0f + ei) * (1.0f + eg));
+                const float fg = __fdividef(1.0f, 1.0f + ef);
+                const float cn = fmaf(fg, c[ub * 8 + j], ig);
+                c[ub * 8 + j] = cn;
+                const float ec = ex2_approx(fminf(cn * (-2.0f * kLog2e), 57.0f));
+                hv[j] = __fdividef(1.0f - ec, (1.0f + eo) * (1.0f + ec));  // sigmoid(o) tanh(c)
+                // dense2 contribution of relu(h) (fp32 FFMA, weights broadcast from smem)
+                const float rj = fmaxf(hv[j], 0.0f);
+                const float *wrow = w2f + (d * kH + ub * 8 + j) * 16;
+#pragma unroll
+                for (int a = 0; a < APAD; a += 4) {
+                  const float4 wv = *reinterpret_cast<const float4 *>(wrow + a);
+                  pl[a] = fmaf(rj, wv.x, pl[a]); pl[a + 1] = fmaf(rj, wv.y, pl[a + 1]);
+                  pl[a + 2] = fmaf(rj, wv.z, pl[a + 2]); pl[a + 3] = fmaf(rj, wv.w, pl[a + 3]);
+                }
+              }
+              if (st < N - 1) store_chunk_split(sm_h + ub * kChunkA, sm_h + 8192 + ub * kChunkA, row, hv);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&bb[B_H]);
+#pragma unroll
+            for (int tt = 0; tt < N; ++tt)
+              if (tt == t) {
+#pragma unroll
+                for (int a = 0; a < APAD; ++a) lg[tt][a] += pl[a];
+              }
+            TL(g, 5 + 4 * (d * N + st));
           }
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(&sm.bars[B_H0 + d]);
-          TL(d, 5 + 2 * st);
         }
 
-        // ---- heads: logits -> Gumbel-max sample -> (fused) physics, reward, outputs ----
-        if (d == 0) {
-          mbar_wait(&sm.bars[B_L], ph_l); ph_l ^= 1;
-          tc_fence_after();
-          TL(d, 12);
-          int au[N], ac[N];
+        // ---- Gumbel-max sampling ----
+        int au[N], ac[N];
+        {
           const uint64_t step = FUSED ? ro.step0 + (uint64_t)it : io.step;
           const uint64_t seed = FUSED ? s.seed : io.seed;
           const int64_t gid0 = FUSED ? s.gid0 : io.gid0;
 #pragma unroll
           for (int t = 0; t < N; ++t) {
-            uint32_t v[16];
-            tmem_ld16(tmem + lane_base + col_l + t * 16, v);
-            tmem_wait_ld();
-            float lg[16], z[16];
-#pragma unroll
-            for (int a = 0; a < 16; ++a) lg[a] = fmaf(__uint_as_float(v[a]), kWInv, b2[a]);
+            float z[APAD];
             const int64_t orow = b * N + t;
             if (!FUSED && io.gumbel != nullptr) {
 #pragma unroll
-              for (int a = 0; a < 16; ++a) z[a] = (a < w.A && mine) ? lg[a] + io.gumbel[orow * w.A + a] : lg[a];
+              for (int a = 0; a < APAD; ++a) z[a] = (a < w.A && mine) ? lg[t][a] + io.gumbel[orow * w.A + a] : lg[t][a];
             } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (4 * j < w.A) {
-                  const uint4 rr = philox_raw(seed, (uint64_t)(gid0 + b), (uint32_t)step, kDomainGumbel, t * 8 + j);
-                  z[4 * j] = lg[4 * j] + bits_to_gumbel(rr.x); z[4 * j + 1] = lg[4 * j + 1] + bits_to_gumbel(rr.y);
-                  z[4 * j + 2] = lg[4 * j + 2] + bits_to_gumbel(rr.z); z[4 * j + 3] = lg[4 * j + 3] + bits_to_gumbel(rr.w);
-                } else {
+              for (int j = 0; j < APAD / 4; ++j) {
+                if (4 * j >= w.A) {  // uniform: no head entries in this block of four
                   z[4 * j] = z[4 * j + 1] = z[4 * j + 2] = z[4 * j + 3] = 0.0f;
+                  continue;
                 }
+                const uint4 rr = philox_raw(seed, (uint64_t)(gid0 + b), (uint32_t)step, kDomainGumbel, t * 8 + j);
+                const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  z[4 * j + q] = (4 * j + q < w.A) ? lg[t][4 * j + q] + bits_to_gumbel(bits[q]) : 0.0f;
               }
             }
             int bu = 0, bc = 0;
             float best = z[0];
 #pragma unroll
-            for (int a = 1; a < 16; ++a)
+            for (int a = 1; a < APAD; ++a)
               if (a < w.A0 && z[a] > best) { best = z[a]; bu = a; }
             if (w.A1 > 0) {
               float bcv = -INFINITY;
 #pragma unroll
-              for (int a = 0; a < 16; ++a)
+              for (int a = 0; a < APAD; ++a)
                 if (a >= w.A0 && a < w.A && z[a] > bcv) { bcv = z[a]; bc = a - w.A0; }
             }
             au[t] = bu; ac[t] = bc;
-            if (t == N - 1) TL(d, 15);
-            sm.act[(row * N + t) * 2] = bu;
-            sm.act[(row * N + t) * 2 + 1] = bc;
+            sm_act[(row * N + t) * 2] = bu;
+            sm_act[(row * N + t) * 2 + 1] = bc;
             if (!FUSED && mine && io.logits != nullptr) {
 #pragma unroll
-              for (int a = 0; a < 16; ++a)
-                if (a < w.A) io.logits[orow * w.A + a] = lg[a];
+              for (int a = 0; a < APAD; ++a)
+                if (a < w.A) io.logits[orow * w.A + a] = lg[t][a];
             }
-          }
-          if (FUSED) {
-            const int64_t toff = (int64_t)it * s.B;
-            bool do_reset = false;
-            Env<float, SC, N> e;
-            float comm[2][10];
-            double ret = 0.0, n_ep = 0.0, n_steps = 0.0;
-            if (mine) {
-              e.load(s, b);
-              e.physics(au, s.max_speed, s.accel);
-              if (SC == kReference) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                  for (int k = 0; k < 10; ++k) comm[i][k] = k == ac[i] ? 1.0f : 0.0f;
-              }
-              float r[N];
-              int coll[N], occ;
-              float md;
-              e.reward(r, coll, occ, md);
-              float sum = 0.0f;
-#pragma unroll
-              for (int i = 0; i < N; ++i) { sum += r[i]; sm.stage_rew[row * N + i] = r[i]; }
-              const float ep_ret = s.ep_ret[b] + sum;
-              const int ts = s.tstep[b] + 1;
-              do_reset = max_episode_len > 0 && ts >= max_episode_len;
-#pragma unroll
-              for (int i = 0; i < N; ++i)
-                e.obs_row(i, sm.stage_obs + row * R + i * D, SC == kReference ? comm[1 - (i & 1)] : nullptr);
-              if (do_reset) {
-                ret = (double)ep_ret; n_ep = 1.0; n_steps = (double)ts;
-                s.ep_ret[b] = 0.0f; s.tstep[b] = 0;
-              } else {
-                s.ep_ret[b] = ep_ret; s.tstep[b] = ts;
-              }
-            }
-            fold_stats(s.stats, ret, n_ep, n_steps);
-            float *g_obs = ro.obs_next != nullptr ? ro.obs_next + (toff + env0) * R : nullptr;
-            float *g_rew = ro.rew != nullptr ? ro.rew + (toff + env0) * N : nullptr;
-            const bool tma_ok = valid == kRows && ((reinterpret_cast<uintptr_t>(g_obs) | reinterpret_cast<uintptr_t>(g_rew)) & 15) == 0;
-            if (g_obs != nullptr || g_rew != nullptr) {
-              if (tma_ok) {
-                fence_proxy_async_smem();
-                bar_sync_n(2, 128);
-                if (tid == 0) {
-                  if (g_obs != nullptr) bulk_store(g_obs, sm.stage_obs, kRows * R * 4);
-                  if (g_rew != nullptr) bulk_store(g_rew, sm.stage_rew, kRows * N * 4);
-                  bulk_commit();
-                  bulk_wait_read_all();
-                }
-              } else {
-                bar_sync_n(2, 128);
-                if (g_obs != nullptr)
-                  for (int i = row; i < valid * R; i += 128) g_obs[i] = sm.stage_obs[i];
-                if (g_rew != nullptr)
-                  for (int i = row; i < valid * N; i += 128) g_rew[i] = sm.stage_rew[i];
-              }
-            }
-            bar_sync_n(2, 128);
-            if (ro.act_u != nullptr)
-              for (int i = row; i < valid * N; i += 128) ro.act_u[(toff + env0) * N + i] = sm.act[i * 2];
-            if (ro.act_c != nullptr)
-              for (int i = row; i < valid * N; i += 128) ro.act_c[(toff + env0) * N + i] = sm.act[i * 2 + 1];
-            if (mine) {
-              if (do_reset) {
-                const uint32_t ep = s.episode[b] + 1u;
-                s.episode[b] = ep;
-                e.reset(s.seed, (uint64_t)(s.gid0 + b), ep);
-                e.store_world(s, b);
-                if (SC == kReference) {
-#pragma unroll
-                  for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int k = 0; k < 10; ++k) comm[i][k] = 0.0f;
-                }
-              }
-              e.store_agents(s, b);
-              if (SC == kReference) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                  for (int k = 0; k < 10; ++k) s.comm[((int64_t)i * 10 + k) * s.B + b] = comm[i][k];
-              }
-            }
-            __threadfence_block();
-          } else {
-            bar_sync_n(2, 128);
-            const int rows = valid * N;
-            if (io.act_u != nullptr)
-              for (int i = row; i < rows; i += 128) io.act_u[env0 * N + i] = sm.act[i * 2];
-            if (io.act_c != nullptr)
-              for (int i = row; i < rows; i += 128) io.act_c[env0 * N + i] = sm.act[i * 2 + 1];
-            if (io.onehot != nullptr)
-              for (int i = row; i < rows * w.A; i += 128) {
-                const int rr = i / w.A, a = i - rr * w.A;
-                const bool hot = a < w.A0 ? (a == sm.act[rr * 2]) : (a - w.A0 == sm.act[rr * 2 + 1]);
-                io.onehot[env0 * N * w.A + i] = hot ? 1.0f : 0.0f;
-              }
           }
         }
-        TL(d, 13);
-        bar_sync_n(1, 256);  // both warpgroups: the state / staging of this iteration is settled
-        TL(d, 14);
+        TL(g, 28);
+
+        if (FUSED) {
+          // ---- World.step + reward + outputs for env row `row` ----
+          const int64_t toff = (int64_t)it * s.B;
+          bool do_reset = false;
+          Env<float, SC, N> e;
+          float comm[2][10];
+          double ret = 0.0, n_ep = 0.0, n_steps = 0.0;
+          if (mine) {
+            e.load(s, b);
+            e.physics(au, s.max_speed, s.accel);
+            if (SC == kReference) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int k = 0; k < 10; ++k) comm[i][k] = k == ac[i] ? 1.0f : 0.0f;
+            }
+            float r[N];
+            int coll[N], occ;
+            float md;
+            e.reward(r, coll, occ, md);
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { sum += r[i]; stage_rew[row * N + i] = r[i]; }
+            const float ep_ret = s.ep_ret[b] + sum;
+            const int ts = s.tstep[b] + 1;
+            do_reset = max_episode_len > 0 && ts >= max_episode_len;
+#pragma unroll
+            for (int i = 0; i < N; ++i) e.obs_row(i, stage_obs + row * R + i * D, SC == kReference ? comm[1 - (i & 1)] : nullptr);
+            if (do_reset) {
+              ret = (double)ep_ret; n_ep = 1.0; n_steps = (double)ts;
+              s.ep_ret[b] = 0.0f; s.tstep[b] = 0;
+            } else {
+              s.ep_ret[b] = ep_ret; s.tstep[b] = ts;
+            }
+          }
+          fold_stats(s.stats, ret, n_ep, n_steps);
+          float *g_obs = ro.obs_next != nullptr ? ro.obs_next + (toff + env0) * R : nullptr;
+          float *g_rew = ro.rew != nullptr ? ro.rew + (toff + env0) * N : nullptr;
+          const bool tma_ok = valid == kRows && ((reinterpret_cast<uintptr_t>(g_obs) | reinterpret_cast<uintptr_t>(g_rew)) & 15) == 0;
+          if (tma_ok) fence_proxy_async_smem();
+          bar_sync_n(1 + g, 128);
+          if (g_obs != nullptr || g_rew != nullptr) {
+            if (tma_ok) {
+              if (row == 0) {
+                if (g_obs != nullptr) bulk_store(g_obs, stage_obs, kRows * R * 4);
+                if (g_rew != nullptr) bulk_store(g_rew, stage_rew, kRows * N * 4);
+                bulk_commit();
+              }
+            } else {
+              if (g_obs != nullptr)
+                for (int i = row; i < valid * R; i += 128) g_obs[i] = stage_obs[i];
+              if (g_rew != nullptr)
+                for (int i = row; i < valid * N; i += 128) g_rew[i] = stage_rew[i];
+            }
+          }
+          if (ro.act_u != nullptr)
+            for (int i = row; i < valid * N; i += 128) ro.act_u[(toff + env0) * N + i] = sm_act[i * 2];
+          if (ro.act_c != nullptr)
+            for (int i = row; i < valid * N; i += 128) ro.act_c[(toff + env0) * N + i] = sm_act[i * 2 + 1];
+          if (mine) {
+            if (do_reset) {  // experiments/run.py:59-60
+              const uint32_t ep = s.episode[b] + 1u;
+              s.episode[b] = ep;
+              e.reset(s.seed, (uint64_t)(s.gid0 + b), ep);
+              e.store_world(s, b);
+              if (SC == kReference) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                  for (int k = 0; k < 10; ++k) comm[i][k] = 0.0f;
+              }
+            }
+            e.store_agents(s, b);
+            if (SC == kReference) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int k = 0; k < 10; ++k) s.comm[((int64_t)i * 10 + k) * s.B + b] = comm[i][k];
+            }
+          }
+          if (row == 0 && tma_ok && (g_obs != nullptr || g_rew != nullptr)) bulk_wait_read_all();
+        } else {
+          bar_sync_n(1 + g, 128);
+          const int rows = valid * N;
+          if (io.act_u != nullptr)
+            for (int i = row; i < rows; i += 128) io.act_u[env0 * N + i] = sm_act[i * 2];
+          if (io.act_c != nullptr)
+            for (int i = row; i < rows; i += 128) io.act_c[env0 * N + i] = sm_act[i * 2 + 1];
+          if (io.onehot != nullptr)
+            for (int i = row; i < rows * w.A; i += 128) {
+              const int rr = i / w.A, a = i - rr * w.A;
+              const bool hot = a < w.A0 ? (a == sm_act[rr * 2]) : (a - w.A0 == sm_act[rr * 2 + 1]);
+              io.onehot[env0 * N * w.A + i] = hot ? 1.0f : 0.0f;
+            }
+        }
+        TL(g, 29);
+        bar_sync_n(1 + g, 128);  // the group's staging (aliases x) and action buffer are free again
+        TL(g, 30);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_free(tmem, 512);
+  if (warp == 8) tmem_free(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -577,17 +589,18 @@ static int sm_count_tc() {
   return n > 0 ? n : 148;
 }
 
-template <int SC, int N, bool FUSED>
+template <int SC, int N, bool FUSED, int APAD>
 static cudaError_t launch_tc_t(const EnvState<float> &s, const TcDev &w, const ActorIO &io, const RolloutIO &ro,
                                int max_episode_len, int64_t nenvs, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(w.bytes, N, w.Kx);
-  cudaError_t e = cudaFuncSetAttribute(k_tc<SC, N, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_tc<SC, N, FUSED, APAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (nenvs + kRows - 1) / kRows;
   const int nsm = sm_count_tc();
-  const int grid = (int)(ntiles < nsm ? ntiles : nsm);
+  const int64_t pairs = (ntiles + 1) / 2;  // every CTA runs two tile pipelines
+  const int grid = (int)(pairs < nsm ? pairs : nsm);
   static const int dbg = getenv("MPE_TC_TIMELINE") != nullptr;
-  k_tc<SC, N, FUSED><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles, dbg);
+  k_tc<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles, dbg);
   return cudaGetLastError();
 }
 
@@ -596,9 +609,12 @@ bool tc_actor_supported(const TcDev &w, int N) { return tc_supported(w) && (N ==
 cudaError_t launch_actor_forward_tc(const TcDev &w, const ActorIO &io, cudaStream_t st) {
   EnvState<float> s{};
   RolloutIO ro;
+  const bool wide = w.A > 8;
   switch (io.N) {
-    case 2: return launch_tc_t<kSpread, 2, false>(s, w, io, ro, 0, io.B, st);
-    case 3: return launch_tc_t<kSpread, 3, false>(s, w, io, ro, 0, io.B, st);
+    case 2: return wide ? launch_tc_t<kSpread, 2, false, 16>(s, w, io, ro, 0, io.B, st)
+                        : launch_tc_t<kSpread, 2, false, 8>(s, w, io, ro, 0, io.B, st);
+    case 3: return wide ? launch_tc_t<kSpread, 3, false, 16>(s, w, io, ro, 0, io.B, st)
+                        : launch_tc_t<kSpread, 3, false, 8>(s, w, io, ro, 0, io.B, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -610,10 +626,10 @@ cudaError_t launch_rollout_tc(const EnvStateAny &a, const TcDev &w, const Rollou
   s.stats = a.stats; s.B = a.B; s.gid0 = a.gid0; s.seed = a.seed; s.max_speed = (float)a.max_speed;
   s.accel = (float)a.accel; s.track = 1;
   ActorIO io;
-  if (a.scenario == kReference) return launch_tc_t<kReference, 2, true>(s, w, io, ro, a.max_episode_len, a.B, st);
-  if (a.scenario == kSpeaker) return launch_tc_t<kSpeaker, 2, true>(s, w, io, ro, a.max_episode_len, a.B, st);
-  if (a.N == 2) return launch_tc_t<kSpread, 2, true>(s, w, io, ro, a.max_episode_len, a.B, st);
-  if (a.N == 3) return launch_tc_t<kSpread, 3, true>(s, w, io, ro, a.max_episode_len, a.B, st);
+  if (a.scenario == kReference) return launch_tc_t<kReference, 2, true, 16>(s, w, io, ro, a.max_episode_len, a.B, st);
+  if (a.scenario == kSpeaker) return launch_tc_t<kSpeaker, 2, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
+  if (a.N == 2) return launch_tc_t<kSpread, 2, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
+  if (a.N == 3) return launch_tc_t<kSpread, 3, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
   return cudaErrorInvalidValue;
 }
 

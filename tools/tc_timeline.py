@@ -20,13 +20,13 @@ for _ in range(3):
     env.rollout(actor, 1, record=True)
 torch.cuda.synchronize()
 lib = _lib.load()
-buf = (C.c_ulonglong * (148 * 96))()
-lib.mpe_debug_tc_timeline(buf, 148 * 96)
-a = np.array(list(buf), dtype=np.int64).reshape(148, 3, 32)
-names = {0: 'WG0', 1: 'WG1', 2: 'MMA'}
+buf = (C.c_ulonglong * (148 * 128))()
+lib.mpe_debug_tc_timeline(buf, 148 * 128)
+a = np.array(list(buf), dtype=np.int64).reshape(148, 4, 32)
+names = {0: 'WG0', 1: 'WG1', 2: 'MMA0', 3: 'MMA1'}
 for cta in (0, 77):
     t0 = a[cta, 0, 0]
     print('--- CTA', cta)
-    for role in range(3):
+    for role in range(4):
         v = a[cta, role]
         print(names[role], ' '.join('%d:%d' % (i, v[i] - t0) for i in range(32) if v[i] > 0))
