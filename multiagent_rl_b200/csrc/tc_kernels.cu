@@ -165,6 +165,57 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // exp(-x) with the exponent clamped so that products of two such terms stay finite
 __device__ __forceinline__ float exp_neg(float x) { return ex2_approx(fminf(-1.4426950408889634f * x, 57.0f)); }
 
+// dense1 epilogue for 32 hidden units of one env row: h1 = relu(D1/16 + b1) -> fp16 hi/lo, 16 packed columns each
+__device__ __forceinline__ void dense1_half(const uint32_t (&v)[32], const float *b1, uint32_t taddr_hi) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 bj = *reinterpret_cast<const float2 *>(b1 + 2 * j);
+    const float a0 = fmaxf(fmaf(__uint_as_float(v[2 * j]), kWInv, bj.x), 0.0f);
+    const float a1 = fmaxf(fmaf(__uint_as_float(v[2 * j + 1]), kWInv, bj.y), 0.0f);
+    __half h0, l0, h1, l1;
+    split_f16(a0, h0, l0);
+    split_f16(a1, h1, l1);
+    hi[j] = pack_h2(h0, h1);
+    lo[j] = pack_h2(l0, l1);
+  }
+  tmem_st16(taddr_hi, hi);
+  tmem_st16(taddr_hi + 32, lo);
+}
+
+// LSTM cell math for 8 units of one env row: v = 32 gate accumulator columns ([i f g o] per unit, scaled by 16),
+// bg = 32 biases pre-multiplied by -log2(e) (x2 for the g gate), c = the 8 cell states, pl = dense2 partial sums.
+// Writes h as an fp16 hi/lo K-chunk of the recurrent A operand when `store_h`.
+template <int APAD>
+__device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float *bg, const float *w2rows, float (&c)[8],
+                                           float (&pl)[APAD], unsigned char *h_chunk, int row, bool store_h) {
+  float hv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 bbv = *reinterpret_cast<const float4 *>(bg + j * 4);
+    const float ei = ex2_approx(fmaf(__uint_as_float(v[4 * j]), -kWInv * kLog2e, bbv.x));
+    const float ef = ex2_approx(fmaf(__uint_as_float(v[4 * j + 1]), -kWInv * kLog2e, bbv.y));
+    const float eg = ex2_approx(fminf(fmaf(__uint_as_float(v[4 * j + 2]), -2.0f * kWInv * kLog2e, bbv.z), 57.0f));
+    const float eo = ex2_approx(fmaf(__uint_as_float(v[4 * j + 3]), -kWInv * kLog2e, bbv.w));
+    // sigmoid(i) tanh(g) = (1 - eg) / ((1 + ei)(1 + eg)); sigmoid(f) = 1 / (1 + ef).  ei/ef/eo may overflow to
+    // +inf (quotient 0); eg/ec are clamped so that 1 - e stays finite.  8 MUFU ops per cell (5 ex2 + 3 rcp).
+    const float ig = __fdividef(1.0f - eg, (1.0f + ei) * (1.0f + eg));
+    const float fg = __fdividef(1.0f, 1.0f + ef);
+    const float cn = fmaf(fg, c[j], ig);
+    c[j] = cn;
+    const float ec = ex2_approx(fminf(cn * (-2.0f * kLog2e), 57.0f));
+    hv[j] = __fdividef(1.0f - ec, (1.0f + eo) * (1.0f + ec));  // sigmoid(o) tanh(c)
+    const float rj = fmaxf(hv[j], 0.0f);  // dense2 contribution of relu(h): fp32 FFMA, weights broadcast from smem
+#pragma unroll
+    for (int a = 0; a < APAD; a += 4) {
+      const float4 wv = *reinterpret_cast<const float4 *>(w2rows + j * 16 + a);
+      pl[a] = fmaf(rj, wv.x, pl[a]); pl[a + 1] = fmaf(rj, wv.y, pl[a + 1]);
+      pl[a + 2] = fmaf(rj, wv.z, pl[a + 2]); pl[a + 3] = fmaf(rj, wv.w, pl[a + 3]);
+    }
+  }
+  if (store_h) store_chunk_split(h_chunk, h_chunk + 8192, row, hv);
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel: two independent tile pipelines per CTA (one per warpgroup), sharing the weight image
 //   warps 0-3 / 4-7 : warpgroup g = 0 / 1, thread r of the group owns env row r of the group's tile
@@ -333,9 +384,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll 1
         for (int d = 0; d < 2; ++d) {
           const float *bg = reinterpret_cast<const float *>(sm_w + w.off_bg) + d * kGateN;
-          float c[kH];
+          float c[4][8];  // cell state of this thread's row: 4 chunks x 8 units
 #pragma unroll
-          for (int u = 0; u < kH; ++u) c[u] = 0.0f;
+          for (int u = 0; u < kH; ++u) c[u >> 3][u & 7] = 0.0f;
 #pragma unroll 1
           for (int st = 0; st < N; ++st) {
             const int t = d == 0 ? st : N - 1 - st;
@@ -346,25 +397,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_wait(&bb[B_D1], ph_d1); ph_d1 ^= 1;
             tc_fence_after();
             TL(g, 2 + 4 * (d * N + st));
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t v[32];
-              tmem_ld32(tmem + lane_base + col_d1 + half * 32, v);
+            {
+              uint32_t v0[32], v1[32];
+              tmem_ld32(tmem + lane_base + col_d1, v0);
               tmem_wait_ld();
-              uint32_t hi[16], lo[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 bj = *reinterpret_cast<const float2 *>(b1 + half * 32 + 2 * j);
-                const float a0 = fmaxf(fmaf(__uint_as_float(v[2 * j]), kWInv, bj.x), 0.0f);
-                const float a1 = fmaxf(fmaf(__uint_as_float(v[2 * j + 1]), kWInv, bj.y), 0.0f);
-                __half h0, l0, h1, l1;
-                split_f16(a0, h0, l0);
-                split_f16(a1, h1, l1);
-                hi[j] = pack_h2(h0, h1);
-                lo[j] = pack_h2(l0, l1);
-              }
-              tmem_st16(tmem + lane_base + col_h1 + half * 16, hi);
-              tmem_st16(tmem + lane_base + col_h1 + 32 + half * 16, lo);
+              tmem_ld32(tmem + lane_base + col_d1 + 32, v1);  // in flight while the first half is converted
+              dense1_half(v0, b1, tmem + lane_base + col_h1);
+              tmem_wait_ld();
+              dense1_half(v1, b1 + 32, tmem + lane_base + col_h1 + 16);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -376,39 +416,27 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_wait(&bb[B_G], ph_g); ph_g ^= 1;
             tc_fence_after();
             TL(g, 4 + 4 * (d * N + st));
-#pragma unroll
-            for (int ub = 0; ub < 4; ++ub) {  // 8 units x [i f g o] = 32 accumulator columns
-              uint32_t v[32];
-              tmem_ld32(tmem + lane_base + ub * 32, v);
+            // Two chunks (2 x 8 units x [i f g o]) per rolled iteration: the loop body stays inside the
+            // instruction cache, the TMEM load of the next chunk flies while this chunk's cell math runs, and
+            // the cell state rotates through c[0..3] so that the live chunk always has compile-time indices.
+            uint32_t va[32], vb[32];
+            tmem_ld32(tmem + lane_base, va);
+#pragma unroll 1
+            for (int up = 0; up < 2; ++up) {
               tmem_wait_ld();
-              float hv[8];
+              tmem_ld32(tmem + lane_base + (2 * up + 1) * 32, vb);
+              lstm_chunk<APAD>(va, bg + (2 * up) * 32, w2f + (d * kH + (2 * up) * 8) * 16, c[0], pl,
+                               sm_h + (2 * up) * kChunkA, row, st < N - 1);
+              tmem_wait_ld();
+              if (up == 0) tmem_ld32(tmem + lane_base + 2 * 32, va);
+              lstm_chunk<APAD>(vb, bg + (2 * up + 1) * 32, w2f + (d * kH + (2 * up + 1) * 8) * 16, c[1], pl,
+                               sm_h + (2 * up + 1) * kChunkA, row, st < N - 1);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                // biases are stored pre-multiplied by -log2(e) (x2 for the g gate): one FFMA yields the ex2 argument
-                const float4 bbv = *reinterpret_cast<const float4 *>(bg + ub * 32 + j * 4);
-                const float ei = ex2_approx(fmaf(__uint_as_float(v[4 * j]), -kWInv * kLog2e, bbv.x));
-                const float ef = ex2_approx(fmaf(__uint_as_float(v[4 * j + 1]), -kWInv * kLog2e, bbv.y));
-                const float eg = ex2_approx(fminf(fmaf(__uint_as_float(v[4 * j + 2]), -2.0f * kWInv * kLog2e, bbv.z), 57.0f));
-                const float eo = ex2_approx(fmaf(__uint_as_float(v[4 * j + 3]), -kWInv * kLog2e, bbv.w));
-                // sigmoid(i) tanh(g) = (1 - eg) / ((1 + ei)(1 + eg)); sigmoid(f) = 1 / (1 + ef).  ei/ef/eo may
-                // overflow to +inf (quotient 0); eg/ec are clamped so that 1 - e stays finite.
-                const float ig = __fdividef(1.0f - eg, (1.0f + ei) * (1.0f + eg));
-                const float fg = __fdividef(1.0f, 1.0f + ef);
-                const float cn = fmaf(fg, c[ub * 8 + j], ig);
-                c[ub * 8 + j] = cn;
-                const float ec = ex2_approx(fminf(cn * (-2.0f * kLog2e), 57.0f));
-                hv[j] = __fdividef(1.0f - ec, (1.0f + eo) * (1.0f + ec));  // sigmoid(o) tanh(c)
-                // dense2 contribution of relu(h) (fp32 FFMA, weights broadcast from smem)
-                const float rj = fmaxf(hv[j], 0.0f);
-                const float *wrow = w2f + (d * kH + ub * 8 + j) * 16;
-#pragma unroll
-                for (int a = 0; a < APAD; a += 4) {
-                  const float4 wv = *reinterpret_cast<const float4 *>(wrow + a);
-                  pl[a] = fmaf(rj, wv.x, pl[a]); pl[a + 1] = fmaf(rj, wv.y, pl[a + 1]);
-                  pl[a + 2] = fmaf(rj, wv.z, pl[a + 2]); pl[a + 3] = fmaf(rj, wv.w, pl[a + 3]);
-                }
+              for (int j = 0; j < 8; ++j) {  // rotate: after two iterations every group is back in place
+                const float t0 = c[0][j], t1 = c[1][j];
+                c[0][j] = c[2][j]; c[1][j] = c[3][j];
+                c[2][j] = t0; c[3][j] = t1;
               }
-              if (st < N - 1) store_chunk_split(sm_h + ub * kChunkA, sm_h + 8192 + ub * kChunkA, row, hv);
             }
             fence_proxy_async_smem();
             tc_fence_before();
