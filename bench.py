@@ -306,6 +306,9 @@ def run_b200(args):
         extras = side_measurements(m, actor, dev, pk, off)
 
     stats_now = D.reduce_return_stats(env.read_stats(), device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     line = {
@@ -319,9 +322,12 @@ def run_b200(args):
                    'actor_weights': 'random init, reference architecture (26,117 params)', 'seed': SEED},
         'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': pk['bf16_tflops_sustained'],
                      'unit': 'TFLOP/s', 'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': None,
-                     'kernel': 'k_rollout<simple_spread,3>', 'peak_source': pk['source'] + ' bf16 sustained',
-                     'note': 'actor GEMMs run as fp32 FFMA in this round (bit-parity path); against the fp32 SIMT '
-                             'peak of %.1f TFLOP/s the fraction is %.3f' % (FP32_SIMT_TFLOPS, tflops / FP32_SIMT_TFLOPS)},
+                     'kernel': 'k_tc<simple_spread,3,fused> (tcgen05 kind::f16, fp16 hi/lo split operands, fp32 TMEM accum)',
+                     'peak_source': pk['source'] + ' bf16 sustained',
+                     'flops_per_env_step': FLOPS_PER_ENV_STEP,
+                     'note': 'algorithmic (fp32-equivalent) FLOPs; every product is issued as 3 fp16 MMAs for fp32-level '
+                             'accuracy, so tensor-pipe work is 3x this; the kernel is bound by the MUFU/issue cost of the '
+                             'LSTM cell math between the GEMMs (see DESIGN.md 4.3), not by the tensor pipe'},
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clk,
         'episode_stats': {k: stats_now[k] for k in ('episodes', 'mean_return', 'std_return')},
     }

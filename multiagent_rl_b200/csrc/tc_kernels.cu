@@ -189,22 +189,32 @@ __device__ __forceinline__ void dense1_half(const uint32_t (&v)[32], const float
 template <int APAD>
 __device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float *bg, const float *w2rows, float (&c)[8],
                                            float (&pl)[APAD], unsigned char *h_chunk, int row, bool store_h) {
-  float hv[8];
+  // written stage by stage over the 8 cells so that the 8 independent dependency chains interleave (ILP 8)
+  float ei[8], ef[8], eg[8], eo[8], hv[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 bbv = *reinterpret_cast<const float4 *>(bg + j * 4);
-    const float ei = ex2_approx(fmaf(__uint_as_float(v[4 * j]), -kWInv * kLog2e, bbv.x));
-    const float ef = ex2_approx(fmaf(__uint_as_float(v[4 * j + 1]), -kWInv * kLog2e, bbv.y));
-    const float eg = ex2_approx(fminf(fmaf(__uint_as_float(v[4 * j + 2]), -2.0f * kWInv * kLog2e, bbv.z), 57.0f));
-    const float eo = ex2_approx(fmaf(__uint_as_float(v[4 * j + 3]), -kWInv * kLog2e, bbv.w));
-    // sigmoid(i) tanh(g) = (1 - eg) / ((1 + ei)(1 + eg)); sigmoid(f) = 1 / (1 + ef).  ei/ef/eo may overflow to
-    // +inf (quotient 0); eg/ec are clamped so that 1 - e stays finite.  8 MUFU ops per cell (5 ex2 + 3 rcp).
-    const float ig = __fdividef(1.0f - eg, (1.0f + ei) * (1.0f + eg));
-    const float fg = __fdividef(1.0f, 1.0f + ef);
-    const float cn = fmaf(fg, c[j], ig);
-    c[j] = cn;
-    const float ec = ex2_approx(fminf(cn * (-2.0f * kLog2e), 57.0f));
-    hv[j] = __fdividef(1.0f - ec, (1.0f + eo) * (1.0f + ec));  // sigmoid(o) tanh(c)
+    ei[j] = fmaf(__uint_as_float(v[4 * j]), -kWInv * kLog2e, bbv.x);
+    ef[j] = fmaf(__uint_as_float(v[4 * j + 1]), -kWInv * kLog2e, bbv.y);
+    eg[j] = fminf(fmaf(__uint_as_float(v[4 * j + 2]), -2.0f * kWInv * kLog2e, bbv.z), 57.0f);
+    eo[j] = fmaf(__uint_as_float(v[4 * j + 3]), -kWInv * kLog2e, bbv.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ei[j] = ex2_approx(ei[j]); ef[j] = ex2_approx(ef[j]); eg[j] = ex2_approx(eg[j]); eo[j] = ex2_approx(eo[j]); }
+  // sigmoid(i) tanh(g) = (1 - eg) / ((1 + ei)(1 + eg)); sigmoid(f) = 1 / (1 + ef).  ei/ef/eo may overflow to
+  // +inf (quotient 0); eg/ec are clamped so that 1 - e stays finite.  8 MUFU ops per cell (5 ex2 + 3 rcp).
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float ig = __fdividef(1.0f - eg[j], (1.0f + ei[j]) * (1.0f + eg[j]));
+    const float fg = __fdividef(1.0f, 1.0f + ef[j]);
+    c[j] = fmaf(fg, c[j], ig);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) eg[j] = ex2_approx(fminf(c[j] * (-2.0f * kLog2e), 57.0f));  // ec
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hv[j] = __fdividef(1.0f - eg[j], (1.0f + eo[j]) * (1.0f + eg[j]));  // sigmoid(o) tanh(c)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
     const float rj = fmaxf(hv[j], 0.0f);  // dense2 contribution of relu(h): fp32 FFMA, weights broadcast from smem
 #pragma unroll
     for (int a = 0; a < APAD; a += 4) {
