@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kActorThreads, 1)
         int au[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) au[i] = sm.act[(tid * N + i) * 2];
-        e.physics(au, s.max_speed, s.accel);
+        e.physics(au, s);
         if (SC == kReference) {
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(kActorThreads, 1)
         float r[N];
         int coll[N], occ;
         float md;
-        e.reward(r, coll, occ, md);
+        e.reward(r, coll, occ, md, s);
         float sum = 0.0f;
 #pragma unroll
         for (int i = 0; i < N; ++i) { sum += r[i]; sm.rew[tid * N + i] = r[i]; }
@@ -568,6 +568,7 @@ static cudaError_t launch_rollout_t(const EnvStateAny &a, const ActorDev &w, con
   s.tstep = a.tstep; s.ep_ret = static_cast<float *>(a.ep_ret); s.comm = static_cast<float *>(a.comm);
   s.stats = a.stats; s.B = a.B; s.gid0 = a.gid0; s.seed = a.seed; s.max_speed = (float)a.max_speed;
   s.accel = (float)a.accel; s.track = 1;
+  set_thresholds<float>(s, a.scenario);
   const int64_t ntiles = (a.B + TB - 1) / TB;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   k_rollout<SC, N, TB, PAD><<<grid, kActorThreads, smem, st>>>(s, w, ro, a.max_episode_len, ntiles);

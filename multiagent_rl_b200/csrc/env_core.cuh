@@ -13,6 +13,9 @@
 // The arithmetic is written in the reference's operation order so that the fp64 instantiation
 // (compiled with -fmad=false) differs from numpy only through exp/log1p rounding.
 #pragma once
+#include <cmath>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mpe {
@@ -48,7 +51,30 @@ struct EnvState {
   T max_speed;        // < 0: None
   T accel;            // < 0: None -> sensitivity 5.0
   int32_t track;      // accumulate episode returns
+  // Exact squared-distance thresholds (set_thresholds): sqrt is monotone and correctly rounded, so
+  //   sqrt(d2) < c  <=>  d2 < t2(c)      and      sqrt(d2) > c  <=>  d2 >= t2gt(c)
+  // which lets the collision / occupancy flags and the far-pair early-out skip the square root bit-exactly.
+  T t2_coll;          // sqrt(d2) < dist_min (0.30)          is_collision
+  T t2_occ;           // sqrt(d2) < 0.1                      occupied landmark
+  T t2_cut;           // sqrt(d2) > dist_min + underflow     contact force is exactly 0 beyond
 };
+
+// smallest x with sqrt(x) >= c  (so that  sqrt(d2) < c  <=>  d2 < x); host, IEEE sqrt
+template <typename T>
+inline T sqrt_lt_threshold(T c) {
+  T x = c * c;
+  while (std::sqrt(x) >= c) x = std::nextafter(x, (T)0);
+  while (std::sqrt(x) < c) x = std::nextafter(x, (T)INFINITY);
+  return x;
+}
+// smallest x with sqrt(x) > c  (so that  sqrt(d2) > c  <=>  d2 >= x)
+template <typename T>
+inline T sqrt_gt_threshold(T c) {
+  T x = c * c;
+  while (std::sqrt(x) > c) x = std::nextafter(x, (T)0);
+  while (!(std::sqrt(x) > c)) x = std::nextafter(x, (T)INFINITY);
+  return x;
+}
 
 template <typename T>
 __device__ __forceinline__ T softplus_pen(T dist, T dist_min) {
@@ -97,6 +123,67 @@ __device__ __forceinline__ void fold_stats(double *stats, double ret, double n_e
     atomicAdd(stats + 2, c);
     atomicAdd(stats + 3, d);
   }
+}
+
+template <typename T>
+inline void set_thresholds(EnvState<T> &s, int scenario) {
+  const T size = scenario == kSpread ? (T)0.15 : (scenario == kReference ? (T)0.05 : (T)0.075);
+  const T dist_min = size + size;
+  s.t2_coll = sqrt_lt_threshold<T>(dist_min);
+  s.t2_occ = sqrt_lt_threshold<T>((T)0.1);
+  s.t2_cut = sqrt_gt_threshold<T>(dist_min + Underflow<T>::v);
+}
+
+// get_collision_force for one close pair: (gx, gy) = contact_force * delta / dist * penetration.
+// double: upstream's operation order (validation build).  float: same formula with the fast exp/log/reciprocal
+// intrinsics - their error (<= 1e-6 relative on a force that is then scaled by dt = 0.1) is far inside the
+// fp32-vs-float64 tolerance, and the pair is already known to be within reach of the softplus.
+template <typename T>
+__device__ __forceinline__ void contact_force(T dx, T dy, T d2, T dist_min, T &gx, T &gy) {
+  const T dist = sqrt(d2);
+  if constexpr (std::is_same<T, float>::value) {
+    const float y = (dist_min - dist) * 1000.0f;  // -(dist - dist_min) / contact_margin
+    const float sp = y > 0.0f ? y + __logf(1.0f + __expf(-y)) : __logf(1.0f + __expf(y));
+    const float sc = __fdividef(100.0f * (sp * 1e-3f), dist);
+    gx = __fmul_rn(dx, sc);  // never contracted into the caller's accumulation: every kernel variant
+    gy = __fmul_rn(dy, sc);  // (thread-per-env, lanes-per-env, fused) produces the same bits
+  } else {
+    const T pen = softplus_pen<T>(dist, dist_min);
+    gx = (T)100 * dx / dist * pen;
+    gy = (T)100 * dy / dist * pen;
+  }
+}
+
+// a*a + b*b and a*b + c with a FIXED choice of which product is fused, so that every kernel variant (thread-
+// per-env, lanes-per-env, fused rollout) rounds identically.  double (built with -fmad=false): numpy's order.
+template <typename T>
+__device__ __forceinline__ T sq2(T a, T b) { return a * a + b * b; }
+template <>
+__device__ __forceinline__ float sq2<float>(float a, float b) { return fmaf(a, a, __fmul_rn(b, b)); }
+template <typename T>
+__device__ __forceinline__ T mad(T a, T b, T c) { return a * b + c; }
+template <>
+__device__ __forceinline__ float mad<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <typename T>
+__device__ __forceinline__ T mul_rn(T a, T b) { return a * b; }
+template <>
+__device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+
+// World.integrate_state for one movable entity (damping 0.25, mass 1, dt 0.1, optional max_speed clip)
+template <typename T>
+__device__ __forceinline__ void integrate_agent(T &px, T &py, T &vx, T &vy, T fx, T fy, T max_speed) {
+  T vxi = mad<T>(fx, (T)0.1, mul_rn<T>(vx, (T)0.75));  // v = v * (1 - damping); v += (f / mass) * dt
+  T vyi = mad<T>(fy, (T)0.1, mul_rn<T>(vy, (T)0.75));
+  if (max_speed >= (T)0) {
+    const T speed = sqrt(sq2<T>(vxi, vyi));
+    if (speed > max_speed) {
+      vxi = vxi / speed * max_speed;
+      vyi = vyi / speed * max_speed;
+    }
+  }
+  vx = vxi; vy = vyi;
+  px = mad<T>(vxi, (T)0.1, px);
+  py = mad<T>(vyi, (T)0.1, py);
 }
 
 template <typename T, int SC, int N>
@@ -167,8 +254,9 @@ struct Env {
   }
 
   // _set_action (one-hot branch) + World.step up to integrate_state.
-  __device__ __forceinline__ void physics(const int *act_u, T max_speed, T accel) {
-    const T sens = accel >= (T)0 ? accel : (T)5.0;
+  __device__ __forceinline__ void physics(const int *act_u, const EnvState<T> &s) {
+    const T max_speed = s.max_speed;
+    const T sens = s.accel >= (T)0 ? s.accel : (T)5.0;
     T fx[N], fy[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -181,17 +269,15 @@ struct Env {
     }
     if (Dm::kCollide) {
       const T dist_min = size_of_agent() + size_of_agent();
-      const T cut = dist_min + Underflow<T>::v;
 #pragma unroll
       for (int a = 0; a < N; ++a) {
 #pragma unroll
         for (int b = a + 1; b < N; ++b) {
           const T dx = px[a] - px[b], dy = py[a] - py[b];
-          const T dist = sqrt(dx * dx + dy * dy);
-          if (!(dist > cut)) {  // beyond `cut` the penalty underflows to exactly 0 (NaN falls through)
-            const T pen = softplus_pen<T>(dist, dist_min);
-            const T gx = (T)100 * dx / dist * pen;
-            const T gy = (T)100 * dy / dist * pen;
+          const T d2 = sq2<T>(dx, dy);
+          if (!(d2 >= s.t2_cut)) {  // beyond the cut the penalty underflows to exactly 0 (NaN falls through)
+            T gx, gy;
+            contact_force<T>(dx, dy, d2, dist_min, gx, gy);
             fx[a] = gx + fx[a]; fy[a] = gy + fy[a];
             fx[b] = -gx + fx[b]; fy[b] = -gy + fy[b];
           }
@@ -201,19 +287,7 @@ struct Env {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       if (!movable(i)) continue;
-      T vxi = vx[i] * (T)0.75, vyi = vy[i] * (T)0.75;
-      vxi += fx[i] * (T)0.1;
-      vyi += fy[i] * (T)0.1;
-      if (max_speed >= (T)0) {
-        const T speed = sqrt(vxi * vxi + vyi * vyi);
-        if (speed > max_speed) {
-          vxi = vxi / speed * max_speed;
-          vyi = vyi / speed * max_speed;
-        }
-      }
-      vx[i] = vxi; vy[i] = vyi;
-      px[i] += vxi * (T)0.1;
-      py[i] += vyi * (T)0.1;
+      integrate_agent<T>(px[i], py[i], vx[i], vy[i], fx[i], fy[i], max_speed);
     }
   }
 
@@ -253,7 +327,7 @@ struct Env {
 
   // Rewards (per agent, world.collaborative = False: experiments/scenarios.py:171) and the
   // integer channels of simple_spread's benchmark_data.
-  __device__ __forceinline__ void reward(T *rew, int *coll, int &occupied, T &min_dists) const {
+  __device__ __forceinline__ void reward(T *rew, int *coll, int &occupied, T &min_dists, const EnvState<T> &s) const {
     occupied = 0;
     min_dists = (T)0;
     if (SC == kSpread) {
@@ -265,26 +339,25 @@ struct Env {
 #pragma unroll
         for (int a = 0; a < N; ++a) {
           const T dx = px[a] - lx[l], dy = py[a] - ly[l];
-          const T d2 = dx * dx + dy * dy;
+          const T d2 = sq2<T>(dx, dy);
           m2 = (a == 0) ? d2 : (d2 < m2 ? d2 : m2);
         }
         const T m = sqrt(m2);
         base -= m;
         min_dists += m;
-        occupied += (m < (T)0.1) ? 1 : 0;
+        occupied += (m2 < s.t2_occ) ? 1 : 0;
       }
-      const T dist_min = size_of_agent() + size_of_agent();
       bool hit[N][N];
 #pragma unroll
       for (int a = 0; a < N; ++a) {
         {  // upstream also tests the agent against itself: dist 0 < dist_min, a constant -1 (NaN: no hit)
           const T zx = px[a] - px[a], zy = py[a] - py[a];
-          hit[a][a] = sqrt(zx * zx + zy * zy) < dist_min;
+          hit[a][a] = sq2<T>(zx, zy) < s.t2_coll;
         }
 #pragma unroll
         for (int b = a + 1; b < N; ++b) {
           const T dx = px[a] - px[b], dy = py[a] - py[b];
-          const bool h = sqrt(dx * dx + dy * dy) < dist_min;
+          const bool h = sq2<T>(dx, dy) < s.t2_coll;  // == sqrt(d2) < dist_min, exactly
           hit[a][b] = h; hit[b][a] = h;
         }
       }
@@ -305,7 +378,7 @@ struct Env {
         const T gx = g == 0 ? lx[0] : (g == 1 ? lx[1] : lx[2]);
         const T gy = g == 0 ? ly[0] : (g == 1 ? ly[1] : ly[2]);
         const T dx = px[1 - i] - gx, dy = py[1 - i] - gy;
-        rew[i] = g < 0 ? (T)0 : -(dx * dx + dy * dy);
+        rew[i] = g < 0 ? (T)0 : -sq2<T>(dx, dy);
         coll[i] = 0;
       }
     } else {
@@ -313,7 +386,7 @@ struct Env {
       const T gx = g == 0 ? lx[0] : (g == 1 ? lx[1] : lx[2]);
       const T gy = g == 0 ? ly[0] : (g == 1 ? ly[1] : ly[2]);
       const T dx = px[1] - gx, dy = py[1] - gy;
-      rew[0] = rew[1] = -(dx * dx + dy * dy);
+      rew[0] = rew[1] = -sq2<T>(dx, dy);
       coll[0] = coll[1] = 0;
     }
   }

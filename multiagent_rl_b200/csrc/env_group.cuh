@@ -1,0 +1,212 @@
+// simple_spread step for larger teams (N = 6, 9, 12): G lanes cooperate on one env, each lane owns A = N / G
+// agents and A landmarks in registers; positions travel between the lanes of an env by warp shuffle.
+//
+// Why: the thread-per-env kernel needs every entity of the env in one thread's registers (255 registers and
+// spills at N >= 9, 8 warps/SM) and walks N(N-1)/2 pairs serially.  Here a lane evaluates only the forces on
+// its OWN agents (each pair is evaluated by both owners - twice the flops, no atomics, G x the parallelism)
+// and needs ~80 registers.  Results are bit-identical to the thread-per-env kernel:
+//   * the force on agent i from the pair {i, j} is 100 (p_i - p_j) / dist * pen for either ordering, because
+//     upstream's f_b = -f with delta = p_a - p_b negates exactly;
+//   * contributions are added in the order of the other agent's index, which is upstream's (a, b)
+//     lexicographic pair order seen from agent i;
+//   * the landmark terms of the reward are summed in landmark order by every lane.
+// Reference rows: World.apply_environment_force / get_collision_force / integrate_state, simple_spread
+// Scenario.reward / benchmark_data (multiagent package, called from experiments/run.py:44) and
+// experiments/scenarios.py:6-20 (observation); make_world(num_agents=n) at experiments/scenarios.py:170.
+#pragma once
+#include "env_core.cuh"
+
+namespace mpe {
+
+template <typename T, int N, int G>
+struct GroupLayout {
+  static constexpr int A = N / G;       // agents (and landmarks) per lane
+  static constexpr int EPW = 32 / G;    // envs per warp
+  static constexpr int LANES = EPW * G; // active lanes
+  static constexpr int D = 4 + 2 * N;
+  static constexpr int R = N * D;
+  static constexpr int kWarpBytes = ((EPW * R + EPW * N) * (int)sizeof(T) + 127) / 128 * 128;
+  static constexpr int kBlockBytes = kWarpBytes * (kStepThreads / 32);
+  static_assert(N % G == 0, "agents must split evenly over the lanes of an env");
+};
+
+template <typename T, int N, int G>
+__global__ void __launch_bounds__(kStepThreads)
+    k_step_grp(EnvState<T> s, const int32_t *__restrict__ act_u, T *__restrict__ obs, T *__restrict__ rew,
+               uint8_t *__restrict__ done, int32_t *__restrict__ info_i, T *__restrict__ info_f) {
+  using GL = GroupLayout<T, N, G>;
+  constexpr int A = GL::A, EPW = GL::EPW, D = GL::D, R = GL::R, L = N;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int el = lane / G, q = lane - el * G;            // env within the warp, lane within the env
+  const int base_lane = el * G;
+  const int64_t b0 = ((int64_t)blockIdx.x * (kStepThreads / 32) + warp) * EPW;
+  const int64_t b = b0 + el;
+  const bool lane_ok = lane < GL::LANES;
+  const bool active = lane_ok && b < s.B;
+  const bool full = b0 + EPW <= s.B;
+  const unsigned FULL = 0xffffffffu;
+
+  T px[A], py[A], vx[A], vy[A], lx[A], ly[A];
+  int au[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    px[k] = py[k] = vx[k] = vy[k] = lx[k] = ly[k] = (T)0;
+    au[k] = 0;
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+      const int i = q * A + k;
+      const Vec4<T> v = ld4(s.pv + ((int64_t)i * s.B + b) * 4);
+      px[k] = v.x; py[k] = v.y; vx[k] = v.z; vy[k] = v.w;
+      const Vec2<T> l = ld2(s.lm + ((int64_t)i * s.B + b) * 2);
+      lx[k] = l.x; ly[k] = l.y;
+      au[k] = act_u[b * N + i];
+    }
+  }
+
+  // ---- _set_action + apply_environment_force on the lane's own agents ----
+  const T sens = s.accel >= (T)0 ? s.accel : (T)5.0;
+  T fx[A], fy[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    const int a = au[k];
+    fx[k] = ((T)0 + ((a == 1 ? (T)1 : (T)0) - (a == 2 ? (T)1 : (T)0))) * sens;
+    fy[k] = ((T)0 + ((a == 3 ? (T)1 : (T)0) - (a == 4 ? (T)1 : (T)0))) * sens;
+  }
+  const T dist_min = (T)0.15 + (T)0.15;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const T pjx = __shfl_sync(FULL, px[j % A], base_lane + j / A);
+    const T pjy = __shfl_sync(FULL, py[j % A], base_lane + j / A);
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+      if (q * A + k == j) continue;
+      const T dx = px[k] - pjx, dy = py[k] - pjy;
+      const T d2 = sq2<T>(dx, dy);
+      if (!(d2 >= s.t2_cut)) {
+        T gx, gy;
+        contact_force<T>(dx, dy, d2, dist_min, gx, gy);
+        fx[k] = gx + fx[k];
+        fy[k] = gy + fy[k];
+      }
+    }
+  }
+  // ---- integrate_state ----
+#pragma unroll
+  for (int k = 0; k < A; ++k) integrate_agent<T>(px[k], py[k], vx[k], vy[k], fx[k], fy[k], s.max_speed);
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < A; ++k) st4(s.pv + ((int64_t)(q * A + k) * s.B + b) * 4, Vec4<T>{px[k], py[k], vx[k], vy[k]});
+  }
+
+  // ---- reward: nearest agent of the lane's own landmarks, collisions of the lane's own agents ----
+  T m2[A];
+  int coll[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) coll[k] = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const T pjx = __shfl_sync(FULL, px[j % A], base_lane + j / A);
+    const T pjy = __shfl_sync(FULL, py[j % A], base_lane + j / A);
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+      const T dx = pjx - lx[k], dy = pjy - ly[k];
+      const T d2 = sq2<T>(dx, dy);
+      m2[k] = (j == 0) ? d2 : (d2 < m2[k] ? d2 : m2[k]);
+      const T cx = pjx - px[k], cy = pjy - py[k];  // includes j == own agent: dist 0 < dist_min (NaN: no hit)
+      coll[k] += (sq2<T>(cx, cy) < s.t2_coll) ? 1 : 0;
+    }
+  }
+  T m[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) m[k] = sqrt(m2[k]);
+  T base = (T)0, md = (T)0;
+  int occ = 0;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {  // landmark order, like upstream's loop
+    const T ml = __shfl_sync(FULL, m[l % A], base_lane + l / A);
+    const T ml2 = __shfl_sync(FULL, m2[l % A], base_lane + l / A);
+    base -= ml;
+    md += ml;
+    occ += (ml2 < s.t2_occ) ? 1 : 0;
+  }
+  T r[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    T rr = base;
+    for (int c = 0; c < coll[k]; ++c) rr -= (T)1;
+    r[k] = rr;
+  }
+  if (s.track) {  // team return = sum over the lanes of the env, added in lane order (convergent shuffles)
+    T sum = (T)0;
+#pragma unroll
+    for (int k = 0; k < A; ++k) sum += r[k];
+    T tot = (T)0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) tot += __shfl_sync(FULL, sum, base_lane + g);
+    if (active && q == 0) { s.ep_ret[b] += tot; s.tstep[b] += 1; }
+  }
+  if (active) {
+    if (info_i != nullptr) {
+#pragma unroll
+      for (int k = 0; k < A; ++k) info_i[b * (N + 1) + q * A + k] = coll[k];
+      if (q == 0) info_i[b * (N + 1) + N] = occ;
+    }
+    if (info_f != nullptr && q == 0) info_f[b] = md;
+  }
+
+  // ---- outputs: rows of the lane's own agents; a warp's envs are one contiguous span of obs / rew ----
+  T *st_obs = reinterpret_cast<T *>(smem + warp * GL::kWarpBytes);
+  T *st_rew = st_obs + EPW * R;
+  const bool obs_tma = full && obs != nullptr && (reinterpret_cast<uintptr_t>(obs + b0 * R) & 15) == 0 &&
+                       ((EPW * R * sizeof(T)) % 16 == 0);
+  const bool rew_tma = full && rew != nullptr && (reinterpret_cast<uintptr_t>(rew + b0 * N) & 15) == 0 &&
+                       ((EPW * N * sizeof(T)) % 16 == 0);
+  if (obs != nullptr) {
+    T *rowbase = obs_tma ? st_obs + el * R : obs + b * R;
+    const bool wr = obs_tma ? lane_ok : active;
+    if (wr) {
+#pragma unroll
+      for (int k = 0; k < A; ++k) {
+        T *row = rowbase + (q * A + k) * D;
+        row[0] = vx[k]; row[1] = vy[k]; row[2] = px[k]; row[3] = py[k];
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const T llx = __shfl_sync(FULL, lx[l % A], base_lane + l / A);
+      const T lly = __shfl_sync(FULL, ly[l % A], base_lane + l / A);
+      if (wr) {
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          T *row = rowbase + (q * A + k) * D;
+          row[4 + 2 * l] = llx - px[k];
+          row[5 + 2 * l] = lly - py[k];
+        }
+      }
+    }
+  }
+  if (rew != nullptr && (rew_tma ? lane_ok : active)) {
+    T *rr = rew_tma ? st_rew + el * N : rew + b * N;
+#pragma unroll
+    for (int k = 0; k < A; ++k) rr[q * A + k] = r[k];
+  }
+  if (obs_tma || rew_tma) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (obs_tma) bulk_store(obs + b0 * R, st_obs, EPW * R * sizeof(T));
+      if (rew_tma) bulk_store(rew + b0 * N, st_rew, EPW * N * sizeof(T));
+      bulk_commit();
+    }
+  }
+  if (done != nullptr && active) {
+#pragma unroll
+    for (int k = 0; k < A; ++k) done[b * N + q * A + k] = 0;
+  }
+  if ((obs_tma || rew_tma) && lane == 0) bulk_wait_read_all();
+}
+
+}  // namespace mpe

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kStepThreads)
     int au[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) au[i] = act_u[b * N + i];
-    e.physics(au, s.max_speed, s.accel);
+    e.physics(au, s);
     e.store_agents(s, b);
     if (SC == kReference) {  // World.update_agent_state: state.c = action.c
 #pragma unroll
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kStepThreads)
     }
     int coll[N], occ;
     T md;
-    e.reward(r, coll, occ, md);
+    e.reward(r, coll, occ, md, s);
     if (s.track) {
       T sum = (T)0;
 #pragma unroll
@@ -238,6 +238,10 @@ __global__ void __launch_bounds__(kStepThreads)
   }
   emit_outputs<T, SC, N>(e, comm, r, rew != nullptr, obs, rew, b0, lane, full, active, smem + warp * SL::kWarpBytes);
 }
+
+}  // namespace mpe
+#include "env_group.cuh"
+namespace mpe {
 
 // ---------------------------------------------------------------------------------------------
 // state injection / readback: caller layout [B][N][2] <-> device SoA.  Runtime N (not hot).
@@ -310,6 +314,7 @@ inline EnvState<T> typed(const EnvStateAny &a) {
   s.max_speed = (T)a.max_speed;
   s.accel = (T)a.accel;
   s.track = a.track;
+  set_thresholds<T>(s, a.scenario);
   return s;
 }
 
@@ -376,6 +381,23 @@ template <typename T>
 cudaError_t launch_step_t(const EnvStateAny &a, const int32_t *act_u, const int32_t *act_c, const void *comm_vec,
                           void *obs, void *rew, uint8_t *done, int32_t *info_i, void *info_f, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
+  if (a.scenario == kSpread && (a.N == 6 || a.N == 9 || a.N == 12)) {  // G lanes per env (env_group.cuh)
+#define GRP(NN, GG)                                                                                                \
+  {                                                                                                                \
+    using GL = GroupLayout<T, NN, GG>;                                                                             \
+    constexpr int sm = GL::kBlockBytes;                                                                            \
+    cudaError_t err = set_smem<T>(k_step_grp<T, NN, GG>, sm);                                                      \
+    if (err != cudaSuccess) return err;                                                                            \
+    const int64_t per_block = (int64_t)GL::EPW * (kStepThreads / 32);                                              \
+    k_step_grp<T, NN, GG><<<(unsigned)((a.B + per_block - 1) / per_block), kStepThreads, sm, st>>>(                \
+        typed<T>(a), act_u, static_cast<T *>(obs), static_cast<T *>(rew), done, info_i, static_cast<T *>(info_f)); \
+    return cudaGetLastError();                                                                                     \
+  }
+    if (a.N == 6) GRP(6, 2)
+    if (a.N == 9) GRP(9, 3)
+    GRP(12, 4)
+#undef GRP
+  }
   const unsigned grid = (unsigned)((a.B + kStepThreads - 1) / kStepThreads);
 #define CALL(SC, NN)                                                                                         \
   {                                                                                                          \

@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           double ret = 0.0, n_ep = 0.0, n_steps = 0.0;
           if (mine) {
             e.load(s, b);
-            e.physics(au, s.max_speed, s.accel);
+            e.physics(au, s);
             if (SC == kReference) {
 #pragma unroll
               for (int i = 0; i < 2; ++i)
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             float r[N];
             int coll[N], occ;
             float md;
-            e.reward(r, coll, occ, md);
+            e.reward(r, coll, occ, md, s);
             float sum = 0.0f;
 #pragma unroll
             for (int i = 0; i < N; ++i) { sum += r[i]; stage_rew[row * N + i] = r[i]; }
@@ -663,6 +663,7 @@ cudaError_t launch_rollout_tc(const EnvStateAny &a, const TcDev &w, const Rollou
   s.tstep = a.tstep; s.ep_ret = static_cast<float *>(a.ep_ret); s.comm = static_cast<float *>(a.comm);
   s.stats = a.stats; s.B = a.B; s.gid0 = a.gid0; s.seed = a.seed; s.max_speed = (float)a.max_speed;
   s.accel = (float)a.accel; s.track = 1;
+  set_thresholds<float>(s, a.scenario);
   ActorIO io;
   if (a.scenario == kReference) return launch_tc_t<kReference, 2, true, 16>(s, w, io, ro, a.max_episode_len, a.B, st);
   if (a.scenario == kSpeaker) return launch_tc_t<kSpeaker, 2, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
