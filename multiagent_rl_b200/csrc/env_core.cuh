@@ -140,14 +140,19 @@ inline void set_thresholds(EnvState<T> &s, int scenario) {
 // fp32-vs-float64 tolerance, and the pair is already known to be within reach of the softplus.
 template <typename T>
 __device__ __forceinline__ void contact_force(T dx, T dy, T d2, T dist_min, T &gx, T &gy) {
-  const T dist = sqrt(d2);
   if constexpr (std::is_same<T, float>::value) {
+    // 3 MUFU ops (rsq, ex2, lg2) and ~12 FP32 ops, branch free: softplus(y) = max(y, 0) + log(1 + exp(-|y|)).
+    // Far pairs give exp -> 0, log(1) = 0, i.e. exactly +-0 (the double build skips them with the same result);
+    // coincident agents give NaN like upstream's 0/0.
+    const float rinv = rsqrtf(d2);
+    const float dist = d2 * rinv;
     const float y = (dist_min - dist) * 1000.0f;  // -(dist - dist_min) / contact_margin
-    const float sp = y > 0.0f ? y + __logf(1.0f + __expf(-y)) : __logf(1.0f + __expf(y));
-    const float sc = __fdividef(100.0f * (sp * 1e-3f), dist);
+    const float sp = fmaxf(y, 0.0f) + __logf(1.0f + __expf(-fabsf(y)));
+    const float sc = (0.1f * sp) * rinv;  // contact_force * (sp * contact_margin) / dist
     gx = __fmul_rn(dx, sc);  // never contracted into the caller's accumulation: every kernel variant
     gy = __fmul_rn(dy, sc);  // (thread-per-env, lanes-per-env, fused) produces the same bits
   } else {
+    const T dist = sqrt(d2);
     const T pen = softplus_pen<T>(dist, dist_min);
     gx = (T)100 * dx / dist * pen;
     gy = (T)100 * dy / dist * pen;
@@ -275,7 +280,8 @@ struct Env {
         for (int b = a + 1; b < N; ++b) {
           const T dx = px[a] - px[b], dy = py[a] - py[b];
           const T d2 = sq2<T>(dx, dy);
-          if (!(d2 >= s.t2_cut)) {  // beyond the cut the penalty underflows to exactly 0 (NaN falls through)
+          // double: skip pairs whose penalty underflows to exactly 0; float: branch-free (adds an exact zero)
+          if (std::is_same<T, float>::value || !(d2 >= s.t2_cut)) {
             T gx, gy;
             contact_force<T>(dx, dy, d2, dist_min, gx, gy);
             fx[a] = gx + fx[a]; fy[a] = gy + fy[a];

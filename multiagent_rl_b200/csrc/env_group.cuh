@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kStepThreads)
       if (q * A + k == j) continue;
       const T dx = px[k] - pjx, dy = py[k] - pjy;
       const T d2 = sq2<T>(dx, dy);
-      if (!(d2 >= s.t2_cut)) {
+      if (std::is_same<T, float>::value || !(d2 >= s.t2_cut)) {
         T gx, gy;
         contact_force<T>(dx, dy, d2, dist_min, gx, gy);
         fx[k] = gx + fx[k];
