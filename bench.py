@@ -376,6 +376,9 @@ def side_measurements(m, actor, dev, pk, off):
     out['actor_forward_only'] = {'envs': 262144, 'agent_steps_per_s': 262144 * N_AGENTS / s,
                                  'tflops': 262144 * FLOPS_PER_ENV_STEP / s / 1e12}
     del env
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import bench_env_configs
+    out['env_step_configs'] = bench_env_configs.run(dev, pk['hbm_gbs'])  # configs 3/4: env-only HBM fractions
     return out
 
 

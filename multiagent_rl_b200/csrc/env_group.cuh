@@ -25,7 +25,12 @@ struct GroupLayout {
   static constexpr int LANES = EPW * G; // active lanes
   static constexpr int D = 4 + 2 * N;
   static constexpr int R = N * D;
-  static constexpr int kWarpBytes = ((EPW * R + EPW * N) * (int)sizeof(T) + 127) / 128 * 128;
+  // Staging rows: when an env's R obs values are a multiple of 16 B, every env gets its own TMA bulk store and
+  // the rows are padded by 16 B so that the lanes of different envs hit different shared-memory banks
+  // (R = 96 or 336 floats would otherwise put every env on the same bank: 16-way conflicts).
+  static constexpr bool kPerEnv = (R * (int)sizeof(T)) % 16 == 0;
+  static constexpr int RS = kPerEnv ? R + 16 / (int)sizeof(T) : R;
+  static constexpr int kWarpBytes = ((EPW * RS + EPW * N) * (int)sizeof(T) + 127) / 128 * 128;
   static constexpr int kBlockBytes = kWarpBytes * (kStepThreads / 32);
   static_assert(N % G == 0, "agents must split evenly over the lanes of an env");
 };
@@ -158,14 +163,15 @@ __global__ void __launch_bounds__(kStepThreads)
   }
 
   // ---- outputs: rows of the lane's own agents; a warp's envs are one contiguous span of obs / rew ----
+  constexpr int RS = GL::RS;
   T *st_obs = reinterpret_cast<T *>(smem + warp * GL::kWarpBytes);
-  T *st_rew = st_obs + EPW * R;
+  T *st_rew = st_obs + EPW * RS;
   const bool obs_tma = full && obs != nullptr && (reinterpret_cast<uintptr_t>(obs + b0 * R) & 15) == 0 &&
-                       ((EPW * R * sizeof(T)) % 16 == 0);
+                       (GL::kPerEnv || (EPW * R * sizeof(T)) % 16 == 0);
   const bool rew_tma = full && rew != nullptr && (reinterpret_cast<uintptr_t>(rew + b0 * N) & 15) == 0 &&
                        ((EPW * N * sizeof(T)) % 16 == 0);
   if (obs != nullptr) {
-    T *rowbase = obs_tma ? st_obs + el * R : obs + b * R;
+    T *rowbase = obs_tma ? st_obs + el * RS : obs + b * R;
     const bool wr = obs_tma ? lane_ok : active;
     if (wr) {
 #pragma unroll
@@ -193,20 +199,30 @@ __global__ void __launch_bounds__(kStepThreads)
 #pragma unroll
     for (int k = 0; k < A; ++k) rr[q * A + k] = r[k];
   }
+  bool issued = false;
   if (obs_tma || rew_tma) {
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
-      if (obs_tma) bulk_store(obs + b0 * R, st_obs, EPW * R * sizeof(T));
-      if (rew_tma) bulk_store(rew + b0 * N, st_rew, EPW * N * sizeof(T));
-      bulk_commit();
+    if (GL::kPerEnv) {
+      if (obs_tma && lane_ok && q == 0) {  // one bulk store per env (rows are padded apart in smem)
+        bulk_store(obs + b * R, st_obs + el * RS, R * sizeof(T));
+        issued = true;
+      }
+    } else if (obs_tma && lane == 0) {
+      bulk_store(obs + b0 * R, st_obs, EPW * R * sizeof(T));
+      issued = true;
     }
+    if (rew_tma && lane == 0) {
+      bulk_store(rew + b0 * N, st_rew, EPW * N * sizeof(T));
+      issued = true;
+    }
+    if (issued) bulk_commit();
   }
   if (done != nullptr && active) {
 #pragma unroll
     for (int k = 0; k < A; ++k) done[b * N + q * A + k] = 0;
   }
-  if ((obs_tma || rew_tma) && lane == 0) bulk_wait_read_all();
+  if (issued) bulk_wait_read_all();
 }
 
 }  // namespace mpe
