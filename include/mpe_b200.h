@@ -167,6 +167,31 @@ int actor_forward_host(MpeActor *actor, const float *obs_host, int64_t B, int32_
 int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *obs_next, float *rew,
                 int32_t *act_u, int32_t *act_c, void *stream);
 
+/* ---- device-resident replay ring: rls/replay_buffer.py:9-91 (ReplayBuffer), fed with the tuple of
+ * experiments/run.py:46,52 (obs_n, action_n_env, rew_shared = sum(rew_n), new_obs_n, float(done)) ---- */
+typedef struct MpeReplay MpeReplay;
+typedef struct {
+  int64_t capacity;    /* ReplayBuffer(size)                                   */
+  int32_t num_agents, obs_dim;
+  int32_t act0, act1;  /* head widths (one-hot actions are rebuilt on sample)  */
+  int32_t device, reserved0;
+} ReplayConfig;
+
+int replay_create(const ReplayConfig *cfg, MpeReplay **out);
+int replay_destroy(MpeReplay *replay);
+int replay_clear(MpeReplay *replay);               /* ReplayBuffer.clear  */
+int64_t replay_len(const MpeReplay *replay);       /* len(buffer)         */
+int64_t replay_next_idx(const MpeReplay *replay);  /* buffer._next_idx    */
+/* ReplayBuffer.add for B env instances, appended in env order: obs / obs_next [B][N][D] fp32, act_u / act_c [B][N]
+ * int32 head indices, rew [B][N] fp32 per-agent rewards (summed to the shared reward), done [B] fp32 or NULL (0). */
+int replay_add(MpeReplay *replay, const float *obs, const int32_t *act_u, const int32_t *act_c, const float *rew,
+               const float *obs_next, const float *done, int64_t B, void *stream);
+/* ReplayBuffer.make_index + sample_index: idx [batch] int64 device indices, or NULL to draw them uniformly with
+ * replacement (Philox keyed by seed and the number of draws so far).  Outputs (each may be NULL): obs / obs_next
+ * [batch][N][D], act_onehot [batch][N][act0+act1], rew [batch], done [batch], idx_out [batch]. */
+int replay_sample(MpeReplay *replay, int64_t batch, const int64_t *idx, uint64_t seed, float *obs, float *act_onehot,
+                  float *rew, float *obs_next, float *done, int64_t *idx_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,11 @@ class MpeDims(C.Structure):
                 ('env_id_offset', C.c_int64)]
 
 
+class ReplayConfig(C.Structure):
+    _fields_ = [('capacity', C.c_int64), ('num_agents', C.c_int32), ('obs_dim', C.c_int32), ('act0', C.c_int32),
+                ('act1', C.c_int32), ('device', C.c_int32), ('reserved0', C.c_int32)]
+
+
 class ActorConfig(C.Structure):
     _fields_ = [('obs_dim', C.c_int32), ('act0', C.c_int32), ('act1', C.c_int32),
                 ('has_model_head', C.c_int32), ('device', C.c_int32), ('reserved0', C.c_int32)]
@@ -66,6 +71,13 @@ SIGNATURES = {
     'actor_forward': (C.c_int, [P, P, C.c_int64, C.c_int32, P, C.c_uint64, C.c_uint64, C.c_int64, P, P, P, P, P, P]),
     'actor_forward_host': (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, P, P, P, P]),
     'mpe_rollout': (C.c_int, [P, P, C.c_int32, C.c_uint64, P, P, P, P, P]),
+    'replay_create': (C.c_int, [C.POINTER(ReplayConfig), C.POINTER(P)]),
+    'replay_destroy': (C.c_int, [P]),
+    'replay_clear': (C.c_int, [P]),
+    'replay_len': (C.c_int64, [P]),
+    'replay_next_idx': (C.c_int64, [P]),
+    'replay_add': (C.c_int, [P, P, P, P, P, P, P, C.c_int64, P]),
+    'replay_sample': (C.c_int, [P, C.c_int64, P, C.c_uint64, P, P, P, P, P, P, P]),
 }
 
 _lib = None

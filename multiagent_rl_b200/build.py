@@ -25,6 +25,7 @@ UNITS = [
     ('env_kernels_f64.cu', ['-fmad=false']),
     ('actor_kernels.cu', []),
     ('tc_kernels.cu', []),
+    ('replay_kernels.cu', []),
     ('cabi.cu', ['-Xcompiler', '-fvisibility=default']),
 ]
 

@@ -11,6 +11,7 @@
 #include "../../include/mpe_b200.h"
 #include "actor_launch.h"
 #include "env_launch.h"
+#include "replay_launch.h"
 
 namespace {
 
@@ -62,6 +63,13 @@ struct MpeActor {
   float *h_obs = nullptr, *h_onehot = nullptr;  // device mirrors for actor_forward_host
   int32_t *h_act_u = nullptr, *h_act_c = nullptr;
   int64_t h_cap = 0;  // capacity in rows (B*N)
+};
+
+struct MpeReplay {
+  mpe::ReplayDev dev;
+  int device = 0;
+  int64_t size = 0, head = 0;  // host-side ring counters (rls/replay_buffer.py: len(_storage), _next_idx)
+  uint64_t draws = 0;          // Philox counter of make_index calls
 };
 
 extern "C" {
@@ -412,6 +420,83 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
     CK(mpe::launch_rollout_tc(env->st, actor->dev.tc, io, static_cast<cudaStream_t>(stream)));
   else
     CK(mpe::launch_rollout(env->st, actor->dev, io, static_cast<cudaStream_t>(stream)));
+  return MPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// replay ring
+// ------------------------------------------------------------------------------------------------
+int replay_create(const ReplayConfig *cfg, MpeReplay **out) {
+  if (cfg == nullptr || out == nullptr) return fail(MPE_EINVAL, "replay_create: null argument");
+  *out = nullptr;
+  if (cfg->capacity <= 0 || cfg->num_agents <= 0 || cfg->num_agents > 32 || cfg->obs_dim <= 0 || cfg->act0 <= 0 ||
+      cfg->act0 > 127 || cfg->act1 < 0 || cfg->act1 > 127)
+    return fail(MPE_EINVAL, "replay_create: bad configuration");
+  DeviceGuard g(cfg->device);
+  if (!g.ok) return fail(MPE_ECUDA, "replay_create: cannot select device");
+  MpeReplay *r = new (std::nothrow) MpeReplay();
+  if (r == nullptr) return fail(MPE_EINVAL, "replay_create: out of host memory");
+  r->device = cfg->device;
+  mpe::ReplayDev &d = r->dev;
+  d.capacity = cfg->capacity; d.N = cfg->num_agents; d.D = cfg->obs_dim; d.A0 = cfg->act0; d.A1 = cfg->act1;
+  const size_t C = (size_t)d.capacity, R = (size_t)d.N * d.D;
+  cudaError_t e = cudaMalloc(&d.obs, C * R * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d.obs_next, C * R * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d.act_u, C * d.N);
+  if (e == cudaSuccess) e = cudaMalloc(&d.act_c, C * d.N);
+  if (e == cudaSuccess) e = cudaMalloc(&d.rew, C * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d.done, C * sizeof(float));
+  if (e != cudaSuccess) {
+    replay_destroy(r);
+    return fail_cuda(e, "replay_create: cudaMalloc");
+  }
+  *out = r;
+  return MPE_OK;
+}
+
+int replay_destroy(MpeReplay *r) {
+  if (r == nullptr) return MPE_OK;
+  DeviceGuard g(r->device);
+  cudaDeviceSynchronize();
+  void *ptrs[] = {r->dev.obs, r->dev.obs_next, r->dev.act_u, r->dev.act_c, r->dev.rew, r->dev.done};
+  for (void *p : ptrs)
+    if (p != nullptr) cudaFree(p);
+  delete r;
+  return MPE_OK;
+}
+
+int replay_clear(MpeReplay *r) {
+  if (r == nullptr) return fail(MPE_EINVAL, "replay_clear: null handle");
+  r->size = 0; r->head = 0;
+  return MPE_OK;
+}
+
+int64_t replay_len(const MpeReplay *r) { return r == nullptr ? 0 : r->size; }
+int64_t replay_next_idx(const MpeReplay *r) { return r == nullptr ? 0 : r->head; }
+
+int replay_add(MpeReplay *r, const float *obs, const int32_t *act_u, const int32_t *act_c, const float *rew,
+               const float *obs_next, const float *done, int64_t B, void *stream) {
+  if (r == nullptr || obs == nullptr || act_u == nullptr || rew == nullptr || obs_next == nullptr)
+    return fail(MPE_EINVAL, "replay_add: null argument");
+  if (B <= 0) return MPE_OK;
+  if (B > r->dev.capacity) return fail(MPE_EINVAL, "replay_add: batch larger than the ring");
+  if (r->dev.A1 > 0 && act_c == nullptr) return fail(MPE_EINVAL, "replay_add: act_c required for a two-head actor");
+  DeviceGuard g(r->device);
+  CK(mpe::launch_replay_add(r->dev, r->head, B, obs, act_u, act_c, rew, obs_next, done, static_cast<cudaStream_t>(stream)));
+  r->head = (r->head + B) % r->dev.capacity;
+  r->size = r->size + B < r->dev.capacity ? r->size + B : r->dev.capacity;
+  return MPE_OK;
+}
+
+int replay_sample(MpeReplay *r, int64_t batch, const int64_t *idx, uint64_t seed, float *obs, float *act_onehot,
+                  float *rew, float *obs_next, float *done, int64_t *idx_out, void *stream) {
+  if (r == nullptr) return fail(MPE_EINVAL, "replay_sample: null handle");
+  if (batch <= 0) return MPE_OK;
+  if (r->size <= 0) return fail(MPE_EINVAL, "replay_sample: the ring is empty");
+  DeviceGuard g(r->device);
+  CK(mpe::launch_replay_sample(r->dev, r->size, batch, idx, seed, r->draws, obs, act_onehot, rew, obs_next, done, idx_out,
+                               static_cast<cudaStream_t>(stream)));
+  if (idx == nullptr) r->draws += 1;
   return MPE_OK;
 }
 

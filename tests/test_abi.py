@@ -12,7 +12,7 @@ from tests.conftest import ROOT
 def _header_functions():
     src = open(os.path.join(ROOT, 'include', 'mpe_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    names = re.findall(r'^\s*(?:const\s+char\s*\*|int)\s*\*?\s*((?:mpe|actor)_\w+)\s*\(', src, flags=re.M)
+    names = re.findall(r'^\s*(?:const\s+char\s*\*|int64_t|int)\s*\*?\s*((?:mpe|actor|replay)_\w+)\s*\(', src, flags=re.M)
     return sorted(set(names))
 
 

@@ -187,3 +187,22 @@ def test_init_state_dict_shapes():
     sd = actor_ref.init_state_dict(21, [5, 10], 0, model_head=True)
     assert sd['dense2_2.module.weight'].shape == (10, 64) and sd['dense3.module.weight'].shape == (21, 64)
     assert sum(v.size for v in actor_ref.init_state_dict(10, 5, 0).values()) == 26117
+
+
+def test_replay_restatement_matches_reference_class():
+    import sys
+    if not os.path.isdir('/root/reference'):
+        pytest.skip('reference tree not present')
+    sys.path.insert(0, '/root/reference')
+    from rls.replay_buffer import ReplayBuffer
+    from oracle import replay_ref
+    rng = np.random.RandomState(0)
+    ref, mine = ReplayBuffer(size=7), replay_ref.ReplayRing(7)
+    for t in range(19):
+        tr = ([rng.randn(4) for _ in range(3)], [np.eye(5)[rng.randint(5)] for _ in range(3)], float(rng.randn()),
+              [rng.randn(4) for _ in range(3)], float(t % 2))
+        ref.add(*tr); mine.add(*tr)
+        assert len(ref) == len(mine) and ref._next_idx == mine._next_idx
+    idx = [0, 6, 3, 3, 1]
+    for a, b in zip(ref.sample_index(idx), mine.sample_index(idx)):
+        assert np.array_equal(a, b)
