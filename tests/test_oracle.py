@@ -199,8 +199,9 @@ def test_replay_restatement_matches_reference_class():
     rng = np.random.RandomState(0)
     ref, mine = ReplayBuffer(size=7), replay_ref.ReplayRing(7)
     for t in range(19):
-        tr = ([rng.randn(4) for _ in range(3)], [np.eye(5)[rng.randint(5)] for _ in range(3)], float(rng.randn()),
-              [rng.randn(4) for _ in range(3)], float(t % 2))
+        # ndarray entries: the reference's np.array(x, copy=False) (replay_buffer.py:44) rejects lists on numpy 2
+        tr = (rng.randn(3, 4), np.eye(5)[rng.randint(5, size=3)], np.float64(rng.randn()), rng.randn(3, 4),
+              np.float64(t % 2))
         ref.add(*tr); mine.add(*tr)
         assert len(ref) == len(mine) and ref._next_idx == mine._next_idx
     idx = [0, 6, 3, 3, 1]
