@@ -74,7 +74,8 @@ void tc_pack(const TcDev &t, const ActorHostWeights &w, unsigned char *img) {
   for (int d = 0; d < 2; ++d)
     for (int g = 0; g < 4; ++g)
       for (int u = 0; u < kH; ++u) {
-        const int row = g * kH + u, n = u * 4 + g;  // packed gate column: unit-major, [i f g o] adjacent
+        // packed gate column: per pair of units (a, b): [i_a i_b f_a f_b g_a g_b o_a o_b]
+        const int row = g * kH + u, n = (u >> 1) * 8 + g * 2 + (u & 1);
         for (int k = 0; k < kHid; ++k) put_split(img, t.off_wih[d][0], t.off_wih[d][1], kGateN, n, k, wih[d][row * kHid + k]);
         for (int k = 0; k < kH; ++k) put_split(img, t.off_whh[d][0], t.off_whh[d][1], kGateN, n, k, whh[d][row * kH + k]);
         bg[d * kGateN + n] = (bih[d][row] + bhh[d][row]) * (g == 2 ? -2.0f : -1.0f) * kLog2e;  // ex2 argument form
@@ -183,44 +184,75 @@ __device__ __forceinline__ void dense1_half(const uint32_t (&v)[32], const float
   tmem_st16(taddr_hi + 32, lo);
 }
 
-// LSTM cell math for 8 units of one env row: v = 32 gate accumulator columns ([i f g o] per unit, scaled by 16),
-// bg = 32 biases pre-multiplied by -log2(e) (x2 for the g gate), c = the 8 cell states, pl = dense2 partial sums.
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot for two lanes of cell math ----
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 pk(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void upk(f2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// LSTM cell math for 8 units of one env row.  v = 32 gate accumulator columns (scaled by 16) in the packed order
+// [i_a i_b f_a f_b g_a g_b o_a o_b] per pair of units (a, b) = (2p, 2p+1), so that the two cells of a pair sit in
+// adjacent registers and every FP32 operation of the cell is one FFMA2/FADD2/FMUL2.  bg = 32 biases in the same
+// order, pre-multiplied by -log2(e) (x2 for the g gate); c = the 4 packed cell-state pairs; pl = packed dense2
+// partial sums.  Per cell: 8 MUFU ops (5 ex2 + 3 rcp; the sigmoid*tanh products share a reciprocal):
+//   sigmoid(i) tanh(g) = (1 - eg) / ((1 + ei)(1 + eg)),  sigmoid(f) = 1 / (1 + ef),  with e* = exp(-x);
+//   ei/ef/eo may overflow to +inf (quotient 0); eg/ec are clamped so that 1 - e stays finite.
 // Writes h as an fp16 hi/lo K-chunk of the recurrent A operand when `store_h`.
 template <int APAD>
-__device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float *bg, const float *w2rows, float (&c)[8],
-                                           float (&pl)[APAD], unsigned char *h_chunk, int row, bool store_h) {
-  // written stage by stage over the 8 cells so that the 8 independent dependency chains interleave (ILP 8)
-  float ei[8], ef[8], eg[8], eo[8], hv[8];
+__device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float *bg, const float *w2rows, f2 (&c)[4],
+                                           f2 (&pl)[APAD / 2], unsigned char *h_chunk, int row, bool store_h) {
+  const f2 ONE = pk(1.0f, 1.0f), NEG1 = pk(-1.0f, -1.0f);
+  const f2 S1 = pk(-kWInv * kLog2e, -kWInv * kLog2e), S2 = pk(-2.0f * kWInv * kLog2e, -2.0f * kWInv * kLog2e);
+  const f2 S3 = pk(-2.0f * kLog2e, -2.0f * kLog2e);
+  float hv[8];
+  f2 pI[4], pF[4], pG[4], pO[4], nG[4];
+  // stage 1: ex2 arguments (FFMA2), exponentials (MUFU), 1 + e / 1 - e (FADD2 / FFMA2)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 bbv = *reinterpret_cast<const float4 *>(bg + j * 4);
-    ei[j] = fmaf(__uint_as_float(v[4 * j]), -kWInv * kLog2e, bbv.x);
-    ef[j] = fmaf(__uint_as_float(v[4 * j + 1]), -kWInv * kLog2e, bbv.y);
-    eg[j] = fminf(fmaf(__uint_as_float(v[4 * j + 2]), -2.0f * kWInv * kLog2e, bbv.z), 57.0f);
-    eo[j] = fmaf(__uint_as_float(v[4 * j + 3]), -kWInv * kLog2e, bbv.w);
+  for (int p = 0; p < 4; ++p) {
+    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(bg + p * 8);      // (b_i pair, b_f pair)
+    const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(bg + p * 8 + 4);  // (b_g pair, b_o pair)
+    const f2 aI = fma2(pk(v[8 * p + 0], v[8 * p + 1]), S1, b0.x), aF = fma2(pk(v[8 * p + 2], v[8 * p + 3]), S1, b0.y);
+    const f2 aG = fma2(pk(v[8 * p + 4], v[8 * p + 5]), S2, b1.x), aO = fma2(pk(v[8 * p + 6], v[8 * p + 7]), S1, b1.y);
+    float x0, x1;
+    upk(aI, x0, x1); const f2 eI = pk(ex2_approx(x0), ex2_approx(x1));
+    upk(aF, x0, x1); const f2 eF = pk(ex2_approx(x0), ex2_approx(x1));
+    upk(aG, x0, x1); const f2 eG = pk(ex2_approx(fminf(x0, 57.0f)), ex2_approx(fminf(x1, 57.0f)));
+    upk(aO, x0, x1); const f2 eO = pk(ex2_approx(x0), ex2_approx(x1));
+    pI[p] = add2(eI, ONE); pF[p] = add2(eF, ONE); pG[p] = add2(eG, ONE); pO[p] = add2(eO, ONE);
+    nG[p] = fma2(eG, NEG1, ONE);
   }
+  // stage 2: c = sigmoid(f) c + sigmoid(i) tanh(g)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { ei[j] = ex2_approx(ei[j]); ef[j] = ex2_approx(ef[j]); eg[j] = ex2_approx(eg[j]); eo[j] = ex2_approx(eo[j]); }
-  // sigmoid(i) tanh(g) = (1 - eg) / ((1 + ei)(1 + eg)); sigmoid(f) = 1 / (1 + ef).  ei/ef/eo may overflow to
-  // +inf (quotient 0); eg/ec are clamped so that 1 - e stays finite.  8 MUFU ops per cell (5 ex2 + 3 rcp).
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float ig = __fdividef(1.0f - eg[j], (1.0f + ei[j]) * (1.0f + eg[j]));
-    const float fg = __fdividef(1.0f, 1.0f + ef[j]);
-    c[j] = fmaf(fg, c[j], ig);
+  for (int p = 0; p < 4; ++p) {
+    float d0, d1, f0, f1;
+    upk(mul2(pI[p], pG[p]), d0, d1);
+    upk(pF[p], f0, f1);
+    const f2 ig = mul2(nG[p], pk(rcp_approx(d0), rcp_approx(d1)));
+    c[p] = fma2(pk(rcp_approx(f0), rcp_approx(f1)), c[p], ig);
   }
+  // stage 3: h = sigmoid(o) tanh(c) = (1 - ec) / ((1 + eo)(1 + ec))
 #pragma unroll
-  for (int j = 0; j < 8; ++j) eg[j] = ex2_approx(fminf(c[j] * (-2.0f * kLog2e), 57.0f));  // ec
-#pragma unroll
-  for (int j = 0; j < 8; ++j) hv[j] = __fdividef(1.0f - eg[j], (1.0f + eo[j]) * (1.0f + eg[j]));  // sigmoid(o) tanh(c)
+  for (int p = 0; p < 4; ++p) {
+    float x0, x1, d0, d1;
+    upk(mul2(c[p], S3), x0, x1);
+    const f2 eC = pk(ex2_approx(fminf(x0, 57.0f)), ex2_approx(fminf(x1, 57.0f)));
+    upk(mul2(pO[p], add2(eC, ONE)), d0, d1);
+    upk(mul2(fma2(eC, NEG1, ONE), pk(rcp_approx(d0), rcp_approx(d1))), hv[2 * p], hv[2 * p + 1]);
+  }
+  // stage 4: dense2 contribution of relu(h): FFMA2 over pairs of head entries, weights broadcast from smem
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float rj = fmaxf(hv[j], 0.0f);  // dense2 contribution of relu(h): fp32 FFMA, weights broadcast from smem
+    const float rj = fmaxf(hv[j], 0.0f);
+    const f2 rr = pk(rj, rj);
 #pragma unroll
     for (int a = 0; a < APAD; a += 4) {
-      const float4 wv = *reinterpret_cast<const float4 *>(w2rows + j * 16 + a);
-      pl[a] = fmaf(rj, wv.x, pl[a]); pl[a + 1] = fmaf(rj, wv.y, pl[a + 1]);
-      pl[a + 2] = fmaf(rj, wv.z, pl[a + 2]); pl[a + 3] = fmaf(rj, wv.w, pl[a + 3]);
+      const ulonglong2 wv = *reinterpret_cast<const ulonglong2 *>(w2rows + j * 16 + a);
+      pl[a / 2] = fma2(rr, wv.x, pl[a / 2]);
+      pl[a / 2 + 1] = fma2(rr, wv.y, pl[a / 2 + 1]);
     }
   }
   if (store_h) store_chunk_split(h_chunk, h_chunk + 8192, row, hv);
@@ -394,15 +426,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll 1
         for (int d = 0; d < 2; ++d) {
           const float *bg = reinterpret_cast<const float *>(sm_w + w.off_bg) + d * kGateN;
-          float c[4][8];  // cell state of this thread's row: 4 chunks x 8 units
+          f2 c[4][4];  // cell state of this thread's row: 4 chunks x 4 packed pairs of units
 #pragma unroll
-          for (int u = 0; u < kH; ++u) c[u >> 3][u & 7] = 0.0f;
+          for (int u = 0; u < 16; ++u) c[u >> 2][u & 3] = 0ull;
 #pragma unroll 1
           for (int st = 0; st < N; ++st) {
             const int t = d == 0 ? st : N - 1 - st;
-            float pl[APAD];  // this cell's dense2 contribution, folded into lg[t] below
+            f2 pl[APAD / 2];  // this cell's dense2 contribution (packed pairs), folded into lg[t] below
 #pragma unroll
-            for (int a = 0; a < APAD; ++a) pl[a] = 0.0f;
+            for (int a = 0; a < APAD / 2; ++a) pl[a] = 0ull;
             // ---- dense1 epilogue: h1 = relu(D1/16 + b1) -> fp16 hi/lo A operand in TMEM ----
             mbar_wait(&bb[B_D1], ph_d1); ph_d1 ^= 1;
             tc_fence_after();
@@ -442,8 +474,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               lstm_chunk<APAD>(vb, bg + (2 * up + 1) * 32, w2f + (d * kH + (2 * up + 1) * 8) * 16, c[1], pl,
                                sm_h + (2 * up + 1) * kChunkA, row, st < N - 1);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {  // rotate: after two iterations every group is back in place
-                const float t0 = c[0][j], t1 = c[1][j];
+              for (int j = 0; j < 4; ++j) {  // rotate: after two iterations every group is back in place
+                const f2 t0 = c[0][j], t1 = c[1][j];
                 c[0][j] = c[2][j]; c[1][j] = c[3][j];
                 c[2][j] = t0; c[3][j] = t1;
               }
@@ -455,7 +487,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int tt = 0; tt < N; ++tt)
               if (tt == t) {
 #pragma unroll
-                for (int a = 0; a < APAD; ++a) lg[tt][a] += pl[a];
+                for (int a = 0; a < APAD / 2; ++a) {
+                  float p0, p1;
+                  upk(pl[a], p0, p1);
+                  lg[tt][2 * a] += p0; lg[tt][2 * a + 1] += p1;
+                }
               }
             TL(g, 5 + 4 * (d * N + st));
           }
