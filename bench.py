@@ -232,6 +232,7 @@ def run_b200(args):
     act = torch.empty((1, B, N_AGENTS), dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    stats_dev = env.stats_tensor()  # aliases the device statistics of this shard
     from multiagent_rl_b200 import _lib
     lib = _lib.load()
 
@@ -261,8 +262,8 @@ def run_b200(args):
         fused_step(t)
         launches += 1
         t += 1
-        if world > 1 and t % EP_LEN == 0:  # the path's only collective: episode-return statistics
-            stats.copy_(torch.from_numpy(env.read_stats()))
+        if world > 1 and t % EP_LEN == 0:  # the path's only collective: episode-return statistics (no host sync)
+            stats.copy_(stats_dev)
             dist.all_reduce(stats)
         ev[k][1].record()
     sync_all()

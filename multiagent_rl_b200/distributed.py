@@ -34,7 +34,9 @@ def init_from_env(backend=None):
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'
         if backend == 'nccl':
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend)
+            dist.init_process_group(backend=backend, device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend=backend)
     return rank, world, local
 
 

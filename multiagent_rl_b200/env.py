@@ -278,6 +278,19 @@ class BatchedMultiAgentEnv(object):
     def track_returns(self, enable=True):
         _lib.check(self._lib.mpe_track_returns(self._h, 1 if enable else 0), 'mpe_track_returns')
 
+    def stats_tensor(self):
+        """Zero-copy float64[4] CUDA tensor aliasing the shard's statistics (for NCCL reductions without a host
+        sync): [sum(return), sum(return^2), n_episodes, n_steps].  Valid while the env is alive."""
+        p = C.c_void_p()
+        _lib.check(self._lib.mpe_stats_ptr(self._h, C.byref(p)), 'mpe_stats_ptr')
+
+        class _Alias(object):
+            __cuda_array_interface__ = {'shape': (4,), 'typestr': '<f8', 'data': (int(p.value), False), 'version': 2}
+        with torch.cuda.device(self.device):
+            t = torch.as_tensor(_Alias(), device=self.device)
+        t._mpe_owner = self  # keep the env (and the device buffer) alive
+        return t
+
     def read_stats(self, clear=False):
         """-> np.array([sum(return), sum(return^2), n_episodes, n_steps]) for this shard (host sync)."""
         out = (C.c_double * 4)()

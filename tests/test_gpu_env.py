@@ -301,7 +301,9 @@ def test_return_tracking_and_stats():
         _, rew, _, _ = env.step(torch.randint(0, 5, (B, 3), dtype=torch.int32, device='cuda'))
         tot += rew.double().sum(1)
     env.reset()
+    alias = env.stats_tensor()
     s = env.read_stats(clear=True)
     assert s[2] == B and s[3] == 25 * B
+    assert float(alias[2]) == 0.0  # zero-copy view of the (now cleared) device statistics
     assert abs(s[0] - float(tot.sum())) < 1e-2 * B and abs(s[1] - float((tot ** 2).sum())) < 1e-1 * B
     assert env.read_stats()[2] == 0
