@@ -24,6 +24,7 @@ struct TcDev {
   int D = 0, Kx = 0, A0 = 0, A1 = 0, A = 0;
   uint32_t off_wih[2][2] = {}, off_whh[2][2] = {}, off_w1[2] = {};
   uint32_t off_w2f = 0, off_bg = 0, off_b1 = 0, off_b2 = 0;
+  float *scratch = nullptr;  // [148*2 pipelines][12 agents][16][128] forward-pass logits shares (teams of > 3 agents)
 };
 
 enum { kImplAuto = 0, kImplSimt = 1, kImplTc = 2 };
@@ -78,6 +79,8 @@ cudaError_t launch_actor_forward(const ActorDev &w, const ActorIO &io, cudaStrea
 void tc_layout(int D, int A0, int A1, TcDev *out);
 void tc_pack(const TcDev &t, const ActorHostWeights &w, unsigned char *host_image);
 bool tc_actor_supported(const TcDev &w, int N);
+bool tc_rollout_supported(const TcDev &w, int N);
+size_t tc_scratch_floats(int sm_count);
 cudaError_t launch_actor_forward_tc(const TcDev &w, const ActorIO &io, cudaStream_t st);
 cudaError_t launch_rollout_tc(const EnvStateAny &env, const TcDev &w, const RolloutIO &io, cudaStream_t st);
 cudaError_t launch_rollout(const EnvStateAny &env, const ActorDev &w, const RolloutIO &io, cudaStream_t st);

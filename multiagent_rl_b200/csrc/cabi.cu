@@ -55,6 +55,11 @@ struct MpeEnv {
   int32_t *h_act_u = nullptr, *h_act_c = nullptr;
   void *h_obs = nullptr, *h_rew = nullptr;
   uint8_t *h_done = nullptr;
+  // scratch of the multi-kernel rollout (teams of > 3 agents): current observations and sampled actions
+  float *r_obs = nullptr;
+  int32_t *r_act = nullptr;
+  bool synced = false;      // all envs are at the same episode step (true after an unmasked reset)
+  int32_t host_tstep = 0;   // that common episode step
 };
 
 struct MpeActor {
@@ -145,7 +150,7 @@ int mpe_destroy(MpeEnv *env) {
   cudaDeviceSynchronize();
   mpe::EnvStateAny &s = env->st;
   void *ptrs[] = {s.pv, s.lm, s.ep_ret, s.comm, s.goal, s.episode, s.tstep, s.stats,
-                  env->h_act_u, env->h_act_c, env->h_obs, env->h_rew, env->h_done};
+                  env->h_act_u, env->h_act_c, env->h_obs, env->h_rew, env->h_done, env->r_obs, env->r_act};
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
   delete env;
@@ -173,7 +178,9 @@ int mpe_seed(MpeEnv *env, uint64_t seed) {
 int mpe_reset(MpeEnv *env, const uint8_t *mask, void *obs_out, void *stream) {
   if (env == nullptr) return fail(MPE_EINVAL, "mpe_reset: null env");
   DeviceGuard g(env->device);
-  CK(mpe::launch_reset(env->st, mask, obs_out, static_cast<cudaStream_t>(stream)));
+  CK(mpe::launch_reset(env->st, mask, obs_out, 0, static_cast<cudaStream_t>(stream)));
+  env->synced = mask == nullptr;  // every env starts an episode together
+  env->host_tstep = mask == nullptr ? 0 : env->host_tstep;
   return MPE_OK;
 }
 
@@ -181,6 +188,7 @@ int mpe_set_state(MpeEnv *env, const void *pos, const void *vel, const void *lm,
   if (env == nullptr) return fail(MPE_EINVAL, "mpe_set_state: null env");
   DeviceGuard g(env->device);
   CK(mpe::launch_set_state(env->st, pos, vel, lm, goal, static_cast<cudaStream_t>(stream)));
+  env->synced = false;
   return MPE_OK;
 }
 
@@ -206,6 +214,7 @@ int mpe_step(MpeEnv *env, const int32_t *act_u, const int32_t *act_c, const void
   DeviceGuard g(env->device);
   CK(mpe::launch_step(env->st, act_u, act_c, comm_vec, obs, rew, done, info_i, info_f,
                       static_cast<cudaStream_t>(stream)));
+  if (env->st.track) env->host_tstep += 1; else env->synced = false;
   return MPE_OK;
 }
 
@@ -280,6 +289,11 @@ int actor_create(const ActorConfig *cfg, MpeActor **out) {
   if (e == cudaSuccess) e = cudaMemset(a->dev.blob, 0, a->dev.blob_floats * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&a->dev.tc.blob, a->dev.tc.bytes);
   if (e == cudaSuccess) e = cudaMemset(a->dev.tc.blob, 0, a->dev.tc.bytes);
+  if (e == cudaSuccess) {
+    int nsm = 0;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device);
+    e = cudaMalloc(&a->dev.tc.scratch, mpe::tc_scratch_floats(nsm > 0 ? nsm : 148) * sizeof(float));
+  }
   if (e != cudaSuccess) {
     delete a;
     return fail_cuda(e, "actor_create: cudaMalloc");
@@ -292,7 +306,7 @@ int actor_destroy(MpeActor *a) {
   if (a == nullptr) return MPE_OK;
   DeviceGuard g(a->device);
   cudaDeviceSynchronize();
-  void *ptrs[] = {a->dev.blob, a->dev.tc.blob, a->h_obs, a->h_onehot, a->h_act_u, a->h_act_c};
+  void *ptrs[] = {a->dev.blob, a->dev.tc.blob, a->dev.tc.scratch, a->h_obs, a->h_onehot, a->h_act_u, a->h_act_c};
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
   delete a;
@@ -355,7 +369,7 @@ int actor_forward(MpeActor *a, const float *obs, int64_t B, int32_t N, const flo
   io.act_u = act_u; io.act_c = act_c; io.onehot = onehot;
   io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
   if (a->dev.impl == mpe::kImplTc && !use_tc(a, N, next_state != nullptr))
-    return fail(MPE_EUNSUPPORTED, "actor_forward: tensor-core path supports 2-3 agents, obs_dim <= 32, no model head");
+    return fail(MPE_EUNSUPPORTED, "actor_forward: tensor-core path supports 2/3/4/6/9/12 agents, obs_dim <= 32, <= 8 head entries for > 3 agents, no model head");
   if (use_tc(a, N, next_state != nullptr))
     CK(mpe::launch_actor_forward_tc(a->dev.tc, io, static_cast<cudaStream_t>(stream)));
   else
@@ -414,12 +428,47 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
   if (!mpe::rollout_supported(env->st.scenario, env->st.N))
     return fail(MPE_EUNSUPPORTED, "mpe_rollout: unsupported scenario / agent count");
   DeviceGuard g(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   mpe::RolloutIO io;
   io.T = T; io.step0 = step0; io.obs_next = obs_next; io.rew = rew; io.act_u = act_u; io.act_c = act_c;
-  if (use_tc(actor, env->st.N, false))
-    CK(mpe::launch_rollout_tc(env->st, actor->dev.tc, io, static_cast<cudaStream_t>(stream)));
-  else
-    CK(mpe::launch_rollout(env->st, actor->dev, io, static_cast<cudaStream_t>(stream)));
+  if (actor->dev.impl != mpe::kImplSimt && mpe::tc_rollout_supported(actor->dev.tc, env->st.N)) {
+    CK(mpe::launch_rollout_tc(env->st, actor->dev.tc, io, st));
+    env->synced = false;
+  } else if (actor->dev.impl != mpe::kImplSimt && env->st.scenario == MPE_SIMPLE_SPREAD &&
+             mpe::tc_actor_supported(actor->dev.tc, env->st.N)) {
+    // Teams of > 3 agents: the same loop as two kernels per step - tensor-core actor (k_tc, actor mode) and the
+    // lanes-per-env step kernel - plus a reset kernel on the steps where an episode can end.
+    mpe::EnvStateAny s = env->st;
+    s.track = 1;
+    const int64_t rows = s.B * s.N;
+    if (env->r_obs == nullptr) {
+      CK(cudaMalloc(&env->r_obs, (size_t)rows * s.D * sizeof(float)));
+      CK(cudaMalloc(&env->r_act, (size_t)rows * sizeof(int32_t)));
+    }
+    CK(mpe::launch_observe(s, env->r_obs, st));
+    const float *cur = env->r_obs;
+    const int L = s.max_episode_len;
+    for (int t = 0; t < T; ++t) {
+      mpe::ActorIO aio;
+      aio.obs = cur; aio.B = s.B; aio.N = s.N; aio.seed = s.seed; aio.step = step0 + (uint64_t)t; aio.gid0 = s.gid0;
+      aio.act_u = act_u != nullptr ? act_u + (int64_t)t * rows : env->r_act;
+      CK(mpe::launch_actor_forward_tc(actor->dev.tc, aio, st));
+      float *o = obs_next != nullptr ? obs_next + (int64_t)t * rows * s.D : env->r_obs;
+      CK(mpe::launch_step(s, aio.act_u, nullptr, nullptr, o, rew != nullptr ? rew + (int64_t)t * rows : nullptr, nullptr,
+                          nullptr, nullptr, st));
+      cur = o;
+      env->host_tstep += 1;
+      const bool may_end = L > 0 && (!env->synced || env->host_tstep >= L);
+      if (may_end) {  // experiments/run.py:59-60; also re-emits the observations the next actor call reads
+        CK(mpe::launch_reset(s, nullptr, env->r_obs, L, st));
+        cur = env->r_obs;
+        if (env->synced) env->host_tstep = 0;
+      }
+    }
+  } else {
+    CK(mpe::launch_rollout(env->st, actor->dev, io, st));
+    env->synced = false;
+  }
   return MPE_OK;
 }
 
@@ -508,8 +557,8 @@ bool env_supported(int scenario, int N) {
   if (scenario == 0) return N == 2 || N == 3 || N == 4 || N == 6 || N == 9 || N == 12;
   return (scenario == 1 || scenario == 2) && N == 2;
 }
-cudaError_t launch_reset(const EnvStateAny &a, const uint8_t *mask, void *obs, cudaStream_t st) {
-  return a.precision == MPE_F64 ? launch_reset_f64(a, mask, obs, st) : launch_reset_f32(a, mask, obs, st);
+cudaError_t launch_reset(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st) {
+  return a.precision == MPE_F64 ? launch_reset_f64(a, mask, obs, auto_len, st) : launch_reset_f32(a, mask, obs, auto_len, st);
 }
 cudaError_t launch_observe(const EnvStateAny &a, void *obs, cudaStream_t st) {
   return a.precision == MPE_F64 ? launch_observe_f64(a, obs, st) : launch_observe_f32(a, obs, st);

@@ -117,7 +117,7 @@ __device__ __forceinline__ void store_comm(const EnvState<T> &s, int64_t b, cons
 // env.reset(): Scenario.reset_world for the masked envs, then (optionally) the observation.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int SC, int N>
-__global__ void __launch_bounds__(kStepThreads) k_reset(EnvState<T> s, const uint8_t *mask, T *obs) {
+__global__ void __launch_bounds__(kStepThreads) k_reset(EnvState<T> s, const uint8_t *mask, T *obs, int auto_len) {
   extern __shared__ __align__(128) unsigned char smem[];
   using SL = StageLayout<T, SC, N>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kStepThreads) k_reset(EnvState<T> s, const uin
   T comm[2][10];
   double ret = 0.0, n_ep = 0.0, n_steps = 0.0;
   if (active) {
-    const bool doit = mask == nullptr || mask[b] != 0;
+    // auto_len > 0: only envs whose episode has reached auto_len steps (experiments/run.py:50,59-60)
+    const bool doit = (mask == nullptr || mask[b] != 0) && (auto_len <= 0 || s.tstep[b] >= auto_len);
     if (doit) {
       const uint32_t ep = s.episode[b] + 1u;
       s.episode[b] = ep;
@@ -346,7 +347,7 @@ inline cudaError_t set_smem(K kernel, int bytes) {
 }
 
 template <typename T>
-cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs, cudaStream_t st) {
+cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
   const unsigned grid = (unsigned)((a.B + kStepThreads - 1) / kStepThreads);
 #define CALL(SC, NN)                                                                          \
@@ -354,7 +355,7 @@ cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs,
     constexpr int sm = StageLayout<T, SC, NN>::kBlockBytes;                                   \
     cudaError_t err = set_smem<T>(k_reset<T, SC, NN>, sm);                                    \
     if (err != cudaSuccess) return err;                                                       \
-    k_reset<T, SC, NN><<<grid, kStepThreads, sm, st>>>(typed<T>(a), mask, static_cast<T *>(obs)); \
+    k_reset<T, SC, NN><<<grid, kStepThreads, sm, st>>>(typed<T>(a), mask, static_cast<T *>(obs), auto_len); \
   }
   MPE_DISPATCH(a, CALL);
 #undef CALL

@@ -2,8 +2,8 @@
 #include "env_kernels.cuh"
 
 namespace mpe {
-cudaError_t launch_reset_f32(const EnvStateAny &a, const uint8_t *mask, void *obs, cudaStream_t st) {
-  return launch_reset_t<float>(a, mask, obs, st);
+cudaError_t launch_reset_f32(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st) {
+  return launch_reset_t<float>(a, mask, obs, auto_len, st);
 }
 cudaError_t launch_observe_f32(const EnvStateAny &a, void *obs, cudaStream_t st) {
   return launch_observe_t<float>(a, obs, st);

@@ -3,8 +3,8 @@
 #include "env_kernels.cuh"
 
 namespace mpe {
-cudaError_t launch_reset_f64(const EnvStateAny &a, const uint8_t *mask, void *obs, cudaStream_t st) {
-  return launch_reset_t<double>(a, mask, obs, st);
+cudaError_t launch_reset_f64(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st) {
+  return launch_reset_t<double>(a, mask, obs, auto_len, st);
 }
 cudaError_t launch_observe_f64(const EnvStateAny &a, void *obs, cudaStream_t st) {
   return launch_observe_t<double>(a, obs, st);

@@ -22,7 +22,7 @@ struct EnvStateAny {
 
 bool env_supported(int scenario, int N);
 
-cudaError_t launch_reset(const EnvStateAny &a, const uint8_t *mask, void *obs, cudaStream_t st);
+cudaError_t launch_reset(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st);
 cudaError_t launch_observe(const EnvStateAny &a, void *obs, cudaStream_t st);
 cudaError_t launch_step(const EnvStateAny &a, const int32_t *act_u, const int32_t *act_c, const void *comm_vec,
                         void *obs, void *rew, uint8_t *done, int32_t *info_i, void *info_f, cudaStream_t st);
@@ -32,7 +32,7 @@ cudaError_t launch_get_state(const EnvStateAny &a, void *pos, void *vel, void *l
 
 // per-precision entry points (defined in env_kernels_f32.cu / env_kernels_f64.cu)
 #define MPE_DECL_PRECISION(SFX)                                                                              \
-  cudaError_t launch_reset_##SFX(const EnvStateAny &, const uint8_t *, void *, cudaStream_t);               \
+  cudaError_t launch_reset_##SFX(const EnvStateAny &, const uint8_t *, void *, int, cudaStream_t);          \
   cudaError_t launch_observe_##SFX(const EnvStateAny &, void *, cudaStream_t);                              \
   cudaError_t launch_step_##SFX(const EnvStateAny &, const int32_t *, const int32_t *, const void *, void *, \
                                 void *, uint8_t *, int32_t *, void *, cudaStream_t);                         \

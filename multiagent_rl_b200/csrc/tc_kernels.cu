@@ -152,10 +152,13 @@ __device__ unsigned long long g_tc_timeline[148 * 128];
 // barriers of one warpgroup's pipeline (indices into its own block of the barrier array)
 enum { B_X = 0, B_D1, B_H1, B_G, B_H, B_PER_WG };
 
-__host__ __device__ inline size_t tc_x_bytes(int N, int Kx) { return (size_t)N * 2 * (Kx / 8) * kChunkA; }
+// observation A operands: all N agents resident for N <= 3; for larger teams a double buffer that is refilled just
+// in time, one cell ahead of the dense1 GEMM that consumes it
+__host__ __device__ inline int tc_x_slots(int N) { return N <= 3 ? N : 2; }
+__host__ __device__ inline size_t tc_x_bytes(int N, int Kx) { return (size_t)tc_x_slots(N) * 2 * (Kx / 8) * kChunkA; }
 __host__ __device__ inline size_t tc_smem_bytes(uint32_t wbytes, int N, int Kx) {
   // weight image + per warpgroup: obs operands, recurrent h operand (hi/lo), action indices; + barriers
-  return (size_t)wbytes + 2 * (tc_x_bytes(N, Kx) + 16384 + (size_t)kRows * N * 2 * 4) + (1 + 2 * B_PER_WG) * 8 + 64;
+  return (size_t)wbytes + 2 * (tc_x_bytes(N, Kx) + 16384 + (size_t)((kRows * N * 2 + 127) / 128 * 128)) + (1 + 2 * B_PER_WG) * 8 + 64;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -276,9 +279,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int D = FUSED ? Dm::D : w.D;
   const int R = N * D;
   const int Kx = w.Kx;
+  constexpr bool kJit = N > 3;  // large teams: actor only, obs operands refilled per cell, logits via global scratch
+  static_assert(!(kJit && FUSED), "the fused env phase keeps every entity in registers: N <= 3");
   const int tid = threadIdx.x, warp = tid >> 5;
   const size_t xb = tc_x_bytes(N, Kx);
-  const size_t wg_bytes = xb + 16384 + (size_t)kRows * N * 2 * 4;
+  const size_t wg_bytes = xb + 16384 + (size_t)((kRows * N * 2 + 127) / 128 * 128);  // x, h, action indices (bytes)
   unsigned char *sm_w = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + w.bytes + 2 * wg_bytes);  // [0] = weights, then 2 x B_PER_WG
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 1 + 2 * B_PER_WG);
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int g = warp >= 8 ? warp - 8 : (tid >> 7);  // pipeline index
   unsigned char *sm_x = smem + w.bytes + g * wg_bytes;
   unsigned char *sm_h = sm_x + xb;                  // [hl][4][128][8] halves
-  int *sm_act = reinterpret_cast<int *>(sm_h + 16384);
+  uint8_t *sm_act = sm_h + 16384;  // [128][N][2] sampled head indices
   float *stage_obs = reinterpret_cast<float *>(sm_x);  // fp32 rows for the TMA store (x is dead by then)
   float *stage_rew = stage_obs + kRows * R;
   uint64_t *bb = bars + 1 + g * B_PER_WG;
@@ -326,12 +331,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           mbar_wait(&bb[B_X], ph_x); ph_x ^= 1;
           tc_fence_after();
           TL(2 + g, 0);
-          auto dense1 = [&](int t) {
-            const unsigned char *xh = sm_x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
+          auto dense1 = [&](int t, int k) {  // k = cell that consumes it; large teams: x lives in slot k & 1
+            const int slot = kJit ? (k & 1) : t;
+            const unsigned char *xh = sm_x + (size_t)(slot * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
             mma3_ss(tmem + col_d1, xh, xl, kChunkA, sm_w + w.off_w1[0], sm_w + w.off_w1[1], kHid * 16, Kx / 16, id_d1, false);
             mma_commit(&bb[B_D1]);
           };
-          dense1(0);
+          dense1(0, 0);
           for (int k = 0; k < 2 * N; ++k) {
             const int d = k / N, st = k - d * N;
             mbar_wait(&bb[B_H1], ph_h1); ph_h1 ^= 1;  // h1 of this cell's agent is in TMEM (and D1 is free again)
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mma_commit(&bb[B_G]);
             if (k + 1 < 2 * N) {  // dense1 of the next cell's agent runs behind the gates on the tensor pipe
               const int d2 = (k + 1) / N, s2 = k + 1 - d2 * N;
-              dense1(d2 == 0 ? s2 : N - 1 - s2);
+              dense1(d2 == 0 ? s2 : N - 1 - s2, k + 1);
             }
             TL(2 + g, 2 + 2 * k);
           }
@@ -377,7 +383,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (int it = 0; it < T; ++it) {
         TL(g, 0);
         // ---- observations -> fp16 hi/lo A operands ----
-        {
+        auto write_x_from_global = [&](int t, int slot) {  // actor mode: obs[b][t][:] -> x operand slot
+          float xr[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) xr[k] = 0.0f;
+          if (mine) {
+            const float *src = io.obs + b * R + t * D;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k < D) xr[k] = src[k];
+          }
+          unsigned char *xh = sm_x + (size_t)(slot * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c * 8 < Kx) {
+              const float v[8] = {xr[c * 8], xr[c * 8 + 1], xr[c * 8 + 2], xr[c * 8 + 3],
+                                  xr[c * 8 + 4], xr[c * 8 + 5], xr[c * 8 + 6], xr[c * 8 + 7]};
+              store_chunk_split(xh + c * kChunkA, xl + c * kChunkA, row, v);
+            }
+          }
+        };
+        if constexpr (kJit) {
+          write_x_from_global(0, 0);  // the first cell's agent; later cells refill one cell ahead
+        } else {
           Env<float, SC, N> e;
           float comm[2][10];
           if (FUSED && mine) {
@@ -391,25 +419,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           }
 #pragma unroll
           for (int t = 0; t < N; ++t) {
-            float xr[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) xr[k] = 0.0f;
             if (FUSED) {
+              float xr[32];
+#pragma unroll
+              for (int k = 0; k < 32; ++k) xr[k] = 0.0f;
               if (mine) e.obs_row(t, xr, SC == kReference ? comm[1 - (t & 1)] : nullptr);
-            } else if (mine) {
-              const float *src = io.obs + b * R + t * D;
+              unsigned char *xh = sm_x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
 #pragma unroll
-              for (int k = 0; k < 32; ++k)
-                if (k < D) xr[k] = src[k];
-            }
-            unsigned char *xh = sm_x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              if (c * 8 < Kx) {
-                const float v[8] = {xr[c * 8], xr[c * 8 + 1], xr[c * 8 + 2], xr[c * 8 + 3],
-                                    xr[c * 8 + 4], xr[c * 8 + 5], xr[c * 8 + 6], xr[c * 8 + 7]};
-                store_chunk_split(xh + c * kChunkA, xl + c * kChunkA, row, v);
+              for (int c = 0; c < 4; ++c) {
+                if (c * 8 < Kx) {
+                  const float v[8] = {xr[c * 8], xr[c * 8 + 1], xr[c * 8 + 2], xr[c * 8 + 3],
+                                      xr[c * 8 + 4], xr[c * 8 + 5], xr[c * 8 + 6], xr[c * 8 + 7]};
+                  store_chunk_split(xh + c * kChunkA, xl + c * kChunkA, row, v);
+                }
               }
+            } else {
+              write_x_from_global(t, t);
             }
           }
         }
@@ -417,11 +442,58 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         mbar_arrive(&bb[B_X]);
         TL(g, 1);
 
-        float lg[N][APAD];  // dense2 accumulators (both directions add into them)
+        // dense2 accumulators (both directions add into them): registers for small teams; for large teams the
+        // forward pass parks its share in a global scratch row and the backward pass finishes + samples per cell
+        constexpr int NLG = kJit ? 1 : N;
+        float lg[NLG][APAD];
 #pragma unroll
-        for (int t = 0; t < N; ++t)
+        for (int t = 0; t < NLG; ++t)
 #pragma unroll
           for (int a = 0; a < APAD; ++a) lg[t][a] = b2[a];
+        float *scratch = kJit ? w.scratch + ((size_t)(blockIdx.x * 2 + g) * N) * APAD * kRows : nullptr;
+        const uint64_t samp_step = FUSED ? ro.step0 + (uint64_t)it : io.step;
+        const uint64_t samp_seed = FUSED ? s.seed : io.seed;
+        const int64_t samp_gid0 = FUSED ? s.gid0 : io.gid0;
+        // F.gumbel_softmax(hard=True) of one agent's logits -> head indices (+ optional logits output)
+        auto sample_agent = [&](int t, const float (&lgt)[APAD], int &bu, int &bc) {
+          float z[APAD];
+          const int64_t orow = b * N + t;
+          if (!FUSED && io.gumbel != nullptr) {
+#pragma unroll
+            for (int a = 0; a < APAD; ++a) z[a] = (a < w.A && mine) ? lgt[a] + io.gumbel[orow * w.A + a] : lgt[a];
+          } else {
+#pragma unroll
+            for (int j = 0; j < APAD / 4; ++j) {
+              if (4 * j >= w.A) {  // uniform: no head entries in this block of four
+                z[4 * j] = z[4 * j + 1] = z[4 * j + 2] = z[4 * j + 3] = 0.0f;
+                continue;
+              }
+              const uint4 rr = philox_raw(samp_seed, (uint64_t)(samp_gid0 + b), (uint32_t)samp_step, kDomainGumbel, t * 8 + j);
+              const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                z[4 * j + q] = (4 * j + q < w.A) ? lgt[4 * j + q] + bits_to_gumbel(bits[q]) : 0.0f;
+            }
+          }
+          bu = 0; bc = 0;
+          float best = z[0];
+#pragma unroll
+          for (int a = 1; a < APAD; ++a)
+            if (a < w.A0 && z[a] > best) { best = z[a]; bu = a; }
+          if (w.A1 > 0) {
+            float bcv = -INFINITY;
+#pragma unroll
+            for (int a = 0; a < APAD; ++a)
+              if (a >= w.A0 && a < w.A && z[a] > bcv) { bcv = z[a]; bc = a - w.A0; }
+          }
+          sm_act[(row * N + t) * 2] = bu;
+          sm_act[(row * N + t) * 2 + 1] = bc;
+          if (!FUSED && mine && io.logits != nullptr) {
+#pragma unroll
+            for (int a = 0; a < APAD; ++a)
+              if (a < w.A) io.logits[orow * w.A + a] = lgt[a];
+          }
+        };
 
 #pragma unroll 1
         for (int d = 0; d < 2; ++d) {
@@ -447,6 +519,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               dense1_half(v0, b1, tmem + lane_base + col_h1);
               tmem_wait_ld();
               dense1_half(v1, b1 + 32, tmem + lane_base + col_h1 + 16);
+            }
+            if constexpr (kJit) {  // obs operand of the NEXT cell's agent (its dense1 GEMM is issued after this arrival)
+              const int k1 = d * N + st + 1;
+              if (k1 < 2 * N) {
+                const int d1 = k1 / N, s1 = k1 - d1 * N;
+                write_x_from_global(d1 == 0 ? s1 : N - 1 - s1, k1 & 1);
+                fence_proxy_async_smem();
+              }
             }
             tmem_wait_st();
             tc_fence_before();
@@ -483,67 +563,42 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&bb[B_H]);
+            if constexpr (kJit) {
+              float *srow = scratch + (size_t)t * APAD * kRows + row;
+              float p[APAD];
 #pragma unroll
-            for (int tt = 0; tt < N; ++tt)
-              if (tt == t) {
+              for (int a = 0; a < APAD / 2; ++a) upk(pl[a], p[2 * a], p[2 * a + 1]);
+              if (d == 0) {  // park the forward share (coalesced over the rows of the tile)
 #pragma unroll
-                for (int a = 0; a < APAD / 2; ++a) {
-                  float p0, p1;
-                  upk(pl[a], p0, p1);
-                  lg[tt][2 * a] += p0; lg[tt][2 * a + 1] += p1;
-                }
+                for (int a = 0; a < APAD; ++a) srow[a * kRows] = p[a];
+              } else {       // backward share arrives: logits of agent t are complete -> sample now
+                float lgt[APAD];
+#pragma unroll
+                for (int a = 0; a < APAD; ++a) lgt[a] = (lg[0][a] + srow[a * kRows]) + p[a];
+                int bu, bc;
+                sample_agent(t, lgt, bu, bc);
               }
+            } else {
+#pragma unroll
+              for (int tt = 0; tt < N; ++tt)
+                if (tt == t) {
+#pragma unroll
+                  for (int a = 0; a < APAD / 2; ++a) {
+                    float p0, p1;
+                    upk(pl[a], p0, p1);
+                    lg[tt][2 * a] += p0; lg[tt][2 * a + 1] += p1;
+                  }
+                }
+            }
             TL(g, 5 + 4 * (d * N + st));
           }
         }
 
-        // ---- Gumbel-max sampling ----
+        // ---- Gumbel-max sampling (small teams; large teams sampled inside the backward pass) ----
         int au[N], ac[N];
-        {
-          const uint64_t step = FUSED ? ro.step0 + (uint64_t)it : io.step;
-          const uint64_t seed = FUSED ? s.seed : io.seed;
-          const int64_t gid0 = FUSED ? s.gid0 : io.gid0;
+        if constexpr (!kJit) {
 #pragma unroll
-          for (int t = 0; t < N; ++t) {
-            float z[APAD];
-            const int64_t orow = b * N + t;
-            if (!FUSED && io.gumbel != nullptr) {
-#pragma unroll
-              for (int a = 0; a < APAD; ++a) z[a] = (a < w.A && mine) ? lg[t][a] + io.gumbel[orow * w.A + a] : lg[t][a];
-            } else {
-#pragma unroll
-              for (int j = 0; j < APAD / 4; ++j) {
-                if (4 * j >= w.A) {  // uniform: no head entries in this block of four
-                  z[4 * j] = z[4 * j + 1] = z[4 * j + 2] = z[4 * j + 3] = 0.0f;
-                  continue;
-                }
-                const uint4 rr = philox_raw(seed, (uint64_t)(gid0 + b), (uint32_t)step, kDomainGumbel, t * 8 + j);
-                const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  z[4 * j + q] = (4 * j + q < w.A) ? lg[t][4 * j + q] + bits_to_gumbel(bits[q]) : 0.0f;
-              }
-            }
-            int bu = 0, bc = 0;
-            float best = z[0];
-#pragma unroll
-            for (int a = 1; a < APAD; ++a)
-              if (a < w.A0 && z[a] > best) { best = z[a]; bu = a; }
-            if (w.A1 > 0) {
-              float bcv = -INFINITY;
-#pragma unroll
-              for (int a = 0; a < APAD; ++a)
-                if (a >= w.A0 && a < w.A && z[a] > bcv) { bcv = z[a]; bc = a - w.A0; }
-            }
-            au[t] = bu; ac[t] = bc;
-            sm_act[(row * N + t) * 2] = bu;
-            sm_act[(row * N + t) * 2 + 1] = bc;
-            if (!FUSED && mine && io.logits != nullptr) {
-#pragma unroll
-              for (int a = 0; a < APAD; ++a)
-                if (a < w.A) io.logits[orow * w.A + a] = lg[t][a];
-            }
-          }
+          for (int t = 0; t < N; ++t) sample_agent(t, lg[t], au[t], ac[t]);
         }
         TL(g, 28);
 
@@ -678,7 +733,11 @@ static cudaError_t launch_tc_t(const EnvState<float> &s, const TcDev &w, const A
   return cudaGetLastError();
 }
 
-bool tc_actor_supported(const TcDev &w, int N) { return tc_supported(w) && (N == 2 || N == 3); }
+bool tc_actor_supported(const TcDev &w, int N) {
+  return tc_supported(w) && (N == 2 || N == 3 || ((N == 4 || N == 6 || N == 9 || N == 12) && w.scratch != nullptr));
+}
+bool tc_rollout_supported(const TcDev &w, int N) { return tc_supported(w) && (N == 2 || N == 3); }
+size_t tc_scratch_floats(int sm_count) { return (size_t)sm_count * 2 * 12 * 16 * kRows; }
 
 cudaError_t launch_actor_forward_tc(const TcDev &w, const ActorIO &io, cudaStream_t st) {
   EnvState<float> s{};
@@ -689,6 +748,10 @@ cudaError_t launch_actor_forward_tc(const TcDev &w, const ActorIO &io, cudaStrea
                         : launch_tc_t<kSpread, 2, false, 8>(s, w, io, ro, 0, io.B, st);
     case 3: return wide ? launch_tc_t<kSpread, 3, false, 16>(s, w, io, ro, 0, io.B, st)
                         : launch_tc_t<kSpread, 3, false, 8>(s, w, io, ro, 0, io.B, st);
+    case 4: return wide ? cudaErrorInvalidValue : launch_tc_t<kSpread, 4, false, 8>(s, w, io, ro, 0, io.B, st);
+    case 6: return wide ? cudaErrorInvalidValue : launch_tc_t<kSpread, 6, false, 8>(s, w, io, ro, 0, io.B, st);
+    case 9: return wide ? cudaErrorInvalidValue : launch_tc_t<kSpread, 9, false, 8>(s, w, io, ro, 0, io.B, st);
+    case 12: return wide ? cudaErrorInvalidValue : launch_tc_t<kSpread, 12, false, 8>(s, w, io, ro, 0, io.B, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -1,0 +1,31 @@
+"""Fused rollout (mpe_rollout, T=25 per call) across scenarios / team sizes: ms per env step and G agent-steps/s."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import multiagent_rl_b200 as m  # noqa: E402
+from oracle import actor_ref  # noqa: E402
+
+CONFIGS = [('simple_spread', None, 65536), ('simple_spread', 6, 65536), ('simple_spread', 9, 32768),
+           ('simple_spread', 12, 32768), ('simple_reference', None, 65536), ('simple_speaker_listener', None, 65536)]
+for scen, n, B in CONFIGS:
+    env = m.make_env(scen, n=n, num_envs=B, batched=True, seed=1, max_episode_len=25)
+    A = [5, 10] if scen == 'simple_reference' else 5
+    actor = m.FusedActor(actor_ref.init_state_dict(env.obs_dim, A, 1), seed=1)
+    env.reset()
+    T = 25
+    env.rollout(actor, T)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        env.rollout(actor, T)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (4 * T)
+    print(json.dumps({'scenario': scen, 'N': env.n, 'envs': B, 'ms_per_env_step': round(ms, 4),
+                      'G_agent_steps_per_s': round(B * env.n / ms / 1e6, 3)}))
+    del env, actor
