@@ -323,7 +323,7 @@ def run_b200(args):
                    'actor_weights': 'random init, reference architecture (26,117 params)', 'seed': SEED},
         'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': pk['bf16_tflops_sustained'],
                      'unit': 'TFLOP/s', 'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': None,
-                     'kernel': 'k_tc<simple_spread,3,fused> (tcgen05 kind::f16, fp16 hi/lo split operands, fp32 TMEM accum)',
+                     'kernel': 'k_tc2<simple_spread,3,fused> (tcgen05 kind::f16, fp16 hi/lo split operands, fp32 TMEM accum)',
                      'peak_source': pk['source'] + ' bf16 sustained',
                      'flops_per_env_step': FLOPS_PER_ENV_STEP,
                      'note': 'algorithmic (fp32-equivalent) FLOPs; every product is issued as 3 fp16 MMAs for fp32-level '

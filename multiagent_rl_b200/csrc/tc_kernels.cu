@@ -709,6 +709,412 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_tc2 (teams of <= 3 agents): the same two tiles per CTA, but BOTH warpgroups work on EVERY cell - warpgroup h
+// takes hidden units 16h..16h+15 of the cell (and 32 of the 64 dense1 columns), and the cells of the two tiles are
+// interleaved in one software pipeline:
+//      E1(A,k)  C(B,k-1)  E1(B,k)  C(A,k)  E1(A,k+1)  C(B,k) ...
+// (E1 = dense1 epilogue -> h1 operand in TMEM, C = LSTM cell math on the gate accumulators).  While all eight warps
+// run the cell math of one tile, the tensor pipe runs the gate GEMM of the other, so no warp ever waits for an MMA
+// in steady state and every SM sub-partition always has two warps in the same MUFU-heavy phase.
+// Warpgroup h owns tile h for everything that is per env (obs operands, sampling, World.step, outputs); the
+// dense2 sums of the units it does not own reach it through a shared-memory exchange buffer.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t tc2_tile_bytes(int N, int Kx, int APAD) {
+  return tc_x_bytes(N, Kx) + 16384 + (size_t)((kRows * N * 2 + 127) / 128 * 128) + (size_t)N * APAD * kRows * 4;
+}
+__host__ __device__ inline size_t tc2_smem_bytes(uint32_t wbytes, int N, int Kx, int APAD) {
+  return (size_t)wbytes + 2 * tc2_tile_bytes(N, Kx, APAD) + (1 + 2 * B_PER_WG) * 8 + 64;
+}
+
+template <int SC, int N, bool FUSED, int APAD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    k_tc2(EnvState<float> s, TcDev w, ActorIO io, RolloutIO ro, int max_episode_len, int64_t ntiles, int dbg) {
+  static_assert(N <= 3, "k_tc2 keeps all obs operands resident");
+  extern __shared__ __align__(128) unsigned char smem[];
+  using Dm = Dims<SC, N>;
+  const int D = FUSED ? Dm::D : w.D;
+  const int R = N * D;
+  const int Kx = w.Kx;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const size_t xb = tc_x_bytes(N, Kx);
+  const size_t tile_bytes = tc2_tile_bytes(N, Kx, APAD);
+  unsigned char *sm_w = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + w.bytes + 2 * tile_bytes);  // [0] = weights, then 2 x B_PER_WG
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 1 + 2 * B_PER_WG);
+  auto tile_smem = [&](int X) { return smem + w.bytes + X * tile_bytes; };
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    for (int g = 0; g < 2; ++g) {
+      uint64_t *bb = bars + 1 + g * B_PER_WG;
+      mbar_init(&bb[B_X], 128);   // the owner warpgroup wrote the tile's obs operands
+      mbar_init(&bb[B_D1], 1);
+      mbar_init(&bb[B_H1], 256);  // both warpgroups converted their half of h1
+      mbar_init(&bb[B_G], 1);
+      mbar_init(&bb[B_H], 256);   // both warpgroups finished their half of the cell
+    }
+    mbar_fence_init();
+    mbar_expect_tx(&bars[0], w.bytes);
+    bulk_load(sm_w, w.blob, w.bytes, &bars[0]);
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int T = FUSED ? ro.T : 1;
+  const uint32_t col_d1 = 128, col_h1 = 192;
+  const int64_t npairs = (ntiles + 1) / 2;
+
+  if (warp >= 8) {
+    // =============================== MMA issuer of tile X = warp - 8 ===============================
+    const int X = warp - 8;
+    if ((tid & 31) == 0) {
+      unsigned char *sm_x = tile_smem(X), *sm_h = sm_x + xb;
+      uint64_t *bb = bars + 1 + X * B_PER_WG;
+      const uint32_t tmem = tmem_base + X * 256;
+      uint32_t ph_x = 0, ph_h1 = 0, ph_h = 0;
+      const uint32_t id_g = make_idesc_f16(128, 128), id_d1 = make_idesc_f16(128, 64);
+      mbar_wait(&bars[0], 0);
+      for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        for (int it = 0; it < T; ++it) {
+          mbar_wait(&bb[B_X], ph_x); ph_x ^= 1;
+          tc_fence_after();
+          auto dense1 = [&](int t) {
+            const unsigned char *xh = sm_x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
+            mma3_ss(tmem + col_d1, xh, xl, kChunkA, sm_w + w.off_w1[0], sm_w + w.off_w1[1], kHid * 16, Kx / 16, id_d1, false);
+            mma_commit(&bb[B_D1]);
+          };
+          dense1(0);
+          for (int k = 0; k < 2 * N; ++k) {
+            const int d = k / N, st = k - d * N;
+            mbar_wait(&bb[B_H1], ph_h1); ph_h1 ^= 1;
+            if (k > 0) { mbar_wait(&bb[B_H], ph_h); ph_h ^= 1; }
+            tc_fence_after();
+            mma3_ts(tmem, tmem + col_h1, tmem + col_h1 + 32, sm_w + w.off_wih[d][0], sm_w + w.off_wih[d][1], kGateN * 16, 4,
+                    id_g, false);
+            if (st > 0) mma3_ss(tmem, sm_h, sm_h + 8192, kChunkA, sm_w + w.off_whh[d][0], sm_w + w.off_whh[d][1], kGateN * 16, 2, id_g, true);
+            mma_commit(&bb[B_G]);
+            if (k + 1 < 2 * N) {
+              const int d2 = (k + 1) / N, s2 = k + 1 - d2 * N;
+              dense1(d2 == 0 ? s2 : N - 1 - s2);
+            }
+          }
+          mbar_wait(&bb[B_H], ph_h); ph_h ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== the eight epilogue warps ===============================
+    const int half = tid >> 7, own = half, row = tid & 127;
+    const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
+    const float *b1 = reinterpret_cast<const float *>(sm_w + w.off_b1);
+    const float *b2 = reinterpret_cast<const float *>(sm_w + w.off_b2);
+    const float *w2f = reinterpret_cast<const float *>(sm_w + w.off_w2f);
+    unsigned char *own_x = tile_smem(own), *own_h = own_x + xb;
+    uint8_t *own_act = own_h + 16384;
+    float *own_xchg = reinterpret_cast<float *>(own_act + (kRows * N * 2 + 127) / 128 * 128);
+    float *stage_obs = reinterpret_cast<float *>(own_x), *stage_rew = stage_obs + kRows * R;
+    uint32_t ph_d1[2] = {0, 0}, ph_g[2] = {0, 0};
+    mbar_wait(&bars[0], 0);
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int64_t tile = pair * 2 + own;                 // the tile this warpgroup owns (may not exist)
+      const int64_t env0 = tile * kRows;
+      const int64_t nb = FUSED ? s.B : io.B;
+      const int valid = tile < ntiles ? (int)((nb - env0) < kRows ? (nb - env0) : kRows) : 0;
+      const bool mine = row < valid;
+      const int64_t b = env0 + row;
+      const bool first_tile = pair == blockIdx.x && row == 0;
+      for (int it = 0; it < T; ++it) {
+        TL(half, 0);
+        // ---- own tile: observations -> fp16 hi/lo A operands ----
+        {
+          Env<float, SC, N> e;
+          float comm[2][10];
+          if (FUSED && mine) {
+            e.load(s, b);
+            if (SC == kReference) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int k = 0; k < 10; ++k) comm[i][k] = s.comm[((int64_t)i * 10 + k) * s.B + b];
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < N; ++t) {
+            float xr[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) xr[k] = 0.0f;
+            if (FUSED) {
+              if (mine) e.obs_row(t, xr, SC == kReference ? comm[1 - (t & 1)] : nullptr);
+            } else if (mine) {
+              const float *src = io.obs + b * R + t * D;
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (k < D) xr[k] = src[k];
+            }
+            unsigned char *xh = own_x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c * 8 < Kx) {
+                const float v[8] = {xr[c * 8], xr[c * 8 + 1], xr[c * 8 + 2], xr[c * 8 + 3],
+                                    xr[c * 8 + 4], xr[c * 8 + 5], xr[c * 8 + 6], xr[c * 8 + 7]};
+                store_chunk_split(xh + c * kChunkA, xl + c * kChunkA, row, v);
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars[1 + own * B_PER_WG + B_X]);
+
+        float lg[N][APAD];  // dense2 sums of the OWN tile's rows over this thread's 16 units (+ bias)
+#pragma unroll
+        for (int t = 0; t < N; ++t)
+#pragma unroll
+          for (int a = 0; a < APAD; ++a) lg[t][a] = b2[a];
+
+        // cell state of this thread's 16 units (2 chunks x 4 packed pairs) for the two tiles; cP belongs to the tile
+        // whose cell is computed in the current half-iteration, the two swap every half-iteration
+        f2 cP[2][4], cQ[2][4];
+        // ---- the interleaved cell pipeline: half-iteration j = (tile X = j & 1, cell k = j >> 1) ----
+#pragma unroll 1
+        for (int j = 0; j <= 4 * N; ++j) {
+          if (j < 4 * N) {  // E1(X, k): dense1 epilogue of this thread's 32 hidden columns
+            const int X = j & 1;
+            uint64_t *bb = bars + 1 + X * B_PER_WG;
+            const uint32_t tmem = tmem_base + X * 256;
+            mbar_wait(&bb[B_D1], ph_d1[X]); ph_d1[X] ^= 1;
+            tc_fence_after();
+            uint32_t v0[32];
+            tmem_ld32(tmem + lane_base + col_d1 + half * 32, v0);
+            tmem_wait_ld();
+            dense1_half(v0, b1 + half * 32, tmem + lane_base + col_h1 + half * 16);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bb[B_H1]);
+            if (j < 13) TL(half, 1 + 2 * j);
+          }
+          if (j >= 1) {  // C(X', k'): the cell whose E1 ran one half-iteration ago
+            const int X = (j - 1) & 1, k = (j - 1) >> 1, d = k / N, st = k - d * N;
+            const int t = d == 0 ? st : N - 1 - st;
+            uint64_t *bb = bars + 1 + X * B_PER_WG;
+            const uint32_t tmem = tmem_base + X * 256;
+            unsigned char *sm_h = tile_smem(X) + xb;
+            if (st == 0) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) cP[0][q] = cP[1][q] = 0ull;
+            }
+            const float *bg = reinterpret_cast<const float *>(sm_w + w.off_bg) + d * kGateN + half * 64;
+            const float *w2d = w2f + (d * kH + half * 16) * 16;
+            f2 pl[APAD / 2];
+#pragma unroll
+            for (int a = 0; a < APAD / 2; ++a) pl[a] = 0ull;
+            mbar_wait(&bb[B_G], ph_g[X]); ph_g[X] ^= 1;
+            tc_fence_after();
+            if (j < 14) TL(half, 2 * j);
+            {
+              uint32_t va[32], vb[32];
+              tmem_ld32(tmem + lane_base + half * 64, va);
+              tmem_wait_ld();
+              tmem_ld32(tmem + lane_base + half * 64 + 32, vb);  // in flight during the first chunk's math
+              lstm_chunk<APAD>(va, bg, w2d, cP[0], pl, sm_h + (2 * half) * kChunkA, row, st < N - 1);
+              tmem_wait_ld();
+              lstm_chunk<APAD>(vb, bg + 32, w2d + 8 * 16, cP[1], pl, sm_h + (2 * half + 1) * kChunkA, row, st < N - 1);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&bb[B_H]);
+            float p[APAD];
+#pragma unroll
+            for (int a = 0; a < APAD / 2; ++a) upk(pl[a], p[2 * a], p[2 * a + 1]);
+            if (X == own) {
+#pragma unroll
+              for (int tt = 0; tt < N; ++tt)
+                if (tt == t) {
+#pragma unroll
+                  for (int a = 0; a < APAD; ++a) lg[tt][a] += p[a];
+                }
+            } else {  // the other tile's rows: park this warpgroup's share for its owner (store, then add)
+              float *xr = reinterpret_cast<float *>(tile_smem(X) + xb + 16384 + (kRows * N * 2 + 127) / 128 * 128) +
+                          (size_t)t * APAD * kRows + row;
+              if (d == 0) {
+#pragma unroll
+                for (int a = 0; a < APAD; ++a) xr[a * kRows] = p[a];
+              } else {
+#pragma unroll
+                for (int a = 0; a < APAD; ++a) xr[a * kRows] += p[a];
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {  // swap the two tiles' cell states
+            const f2 t0 = cP[0][q], t1 = cP[1][q];
+            cP[0][q] = cQ[0][q]; cP[1][q] = cQ[1][q];
+            cQ[0][q] = t0; cQ[1][q] = t1;
+          }
+        }
+        TL(half, 28);
+        bar_sync_n(1, 256);  // the exchange buffers are complete
+
+        // ---- own tile: Gumbel-max sampling ----
+        int au[N], ac[N];
+        {
+          const uint64_t step = FUSED ? ro.step0 + (uint64_t)it : io.step;
+          const uint64_t seed = FUSED ? s.seed : io.seed;
+          const int64_t gid0 = FUSED ? s.gid0 : io.gid0;
+#pragma unroll
+          for (int t = 0; t < N; ++t) {
+            float z[APAD];
+#pragma unroll
+            for (int a = 0; a < APAD; ++a) lg[t][a] += own_xchg[((size_t)t * APAD + a) * kRows + row];
+            const int64_t orow = b * N + t;
+            if (!FUSED && io.gumbel != nullptr) {
+#pragma unroll
+              for (int a = 0; a < APAD; ++a) z[a] = (a < w.A && mine) ? lg[t][a] + io.gumbel[orow * w.A + a] : lg[t][a];
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < APAD / 4; ++jj) {
+                if (4 * jj >= w.A) {
+                  z[4 * jj] = z[4 * jj + 1] = z[4 * jj + 2] = z[4 * jj + 3] = 0.0f;
+                  continue;
+                }
+                const uint4 rr = philox_raw(seed, (uint64_t)(gid0 + b), (uint32_t)step, kDomainGumbel, t * 8 + jj);
+                const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  z[4 * jj + q] = (4 * jj + q < w.A) ? lg[t][4 * jj + q] + bits_to_gumbel(bits[q]) : 0.0f;
+              }
+            }
+            int bu = 0, bc = 0;
+            float best = z[0];
+#pragma unroll
+            for (int a = 1; a < APAD; ++a)
+              if (a < w.A0 && z[a] > best) { best = z[a]; bu = a; }
+            if (w.A1 > 0) {
+              float bcv = -INFINITY;
+#pragma unroll
+              for (int a = 0; a < APAD; ++a)
+                if (a >= w.A0 && a < w.A && z[a] > bcv) { bcv = z[a]; bc = a - w.A0; }
+            }
+            au[t] = bu; ac[t] = bc;
+            own_act[(row * N + t) * 2] = (uint8_t)bu;
+            own_act[(row * N + t) * 2 + 1] = (uint8_t)bc;
+            if (!FUSED && mine && io.logits != nullptr) {
+#pragma unroll
+              for (int a = 0; a < APAD; ++a)
+                if (a < w.A) io.logits[orow * w.A + a] = lg[t][a];
+            }
+          }
+        }
+
+        if (FUSED) {
+          // ---- own tile: World.step + reward + outputs for env row `row` ----
+          const int64_t toff = (int64_t)it * s.B;
+          bool do_reset = false;
+          Env<float, SC, N> e;
+          float comm[2][10];
+          double ret = 0.0, n_ep = 0.0, n_steps = 0.0;
+          if (mine) {
+            e.load(s, b);
+            e.physics(au, s);
+            if (SC == kReference) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int k = 0; k < 10; ++k) comm[i][k] = k == ac[i] ? 1.0f : 0.0f;
+            }
+            float r[N];
+            int coll[N], occ;
+            float md;
+            e.reward(r, coll, occ, md, s);
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { sum += r[i]; stage_rew[row * N + i] = r[i]; }
+            const float ep_ret = s.ep_ret[b] + sum;
+            const int ts = s.tstep[b] + 1;
+            do_reset = max_episode_len > 0 && ts >= max_episode_len;
+#pragma unroll
+            for (int i = 0; i < N; ++i) e.obs_row(i, stage_obs + row * R + i * D, SC == kReference ? comm[1 - (i & 1)] : nullptr);
+            if (do_reset) {
+              ret = (double)ep_ret; n_ep = 1.0; n_steps = (double)ts;
+              s.ep_ret[b] = 0.0f; s.tstep[b] = 0;
+            } else {
+              s.ep_ret[b] = ep_ret; s.tstep[b] = ts;
+            }
+          }
+          fold_stats(s.stats, ret, n_ep, n_steps);
+          float *g_obs = (ro.obs_next != nullptr && valid > 0) ? ro.obs_next + (toff + env0) * R : nullptr;
+          float *g_rew = (ro.rew != nullptr && valid > 0) ? ro.rew + (toff + env0) * N : nullptr;
+          const bool tma_ok = valid == kRows && ((reinterpret_cast<uintptr_t>(g_obs) | reinterpret_cast<uintptr_t>(g_rew)) & 15) == 0;
+          if (tma_ok) fence_proxy_async_smem();
+          bar_sync_n(2 + own, 128);
+          if (g_obs != nullptr || g_rew != nullptr) {
+            if (tma_ok) {
+              if (row == 0) {
+                if (g_obs != nullptr) bulk_store(g_obs, stage_obs, kRows * R * 4);
+                if (g_rew != nullptr) bulk_store(g_rew, stage_rew, kRows * N * 4);
+                bulk_commit();
+              }
+            } else {
+              if (g_obs != nullptr)
+                for (int i = row; i < valid * R; i += 128) g_obs[i] = stage_obs[i];
+              if (g_rew != nullptr)
+                for (int i = row; i < valid * N; i += 128) g_rew[i] = stage_rew[i];
+            }
+          }
+          if (ro.act_u != nullptr)
+            for (int i = row; i < valid * N; i += 128) ro.act_u[(toff + env0) * N + i] = own_act[i * 2];
+          if (ro.act_c != nullptr)
+            for (int i = row; i < valid * N; i += 128) ro.act_c[(toff + env0) * N + i] = own_act[i * 2 + 1];
+          if (mine) {
+            if (do_reset) {  // experiments/run.py:59-60
+              const uint32_t ep = s.episode[b] + 1u;
+              s.episode[b] = ep;
+              e.reset(s.seed, (uint64_t)(s.gid0 + b), ep);
+              e.store_world(s, b);
+              if (SC == kReference) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                  for (int k = 0; k < 10; ++k) comm[i][k] = 0.0f;
+              }
+            }
+            e.store_agents(s, b);
+            if (SC == kReference) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int k = 0; k < 10; ++k) s.comm[((int64_t)i * 10 + k) * s.B + b] = comm[i][k];
+            }
+          }
+          if (row == 0 && tma_ok && (g_obs != nullptr || g_rew != nullptr)) bulk_wait_read_all();
+        } else {
+          bar_sync_n(2 + own, 128);
+          const int rows = valid * N;
+          if (io.act_u != nullptr)
+            for (int i = row; i < rows; i += 128) io.act_u[env0 * N + i] = own_act[i * 2];
+          if (io.act_c != nullptr)
+            for (int i = row; i < rows; i += 128) io.act_c[env0 * N + i] = own_act[i * 2 + 1];
+          if (io.onehot != nullptr)
+            for (int i = row; i < rows * w.A; i += 128) {
+              const int rr = i / w.A, a = i - rr * w.A;
+              const bool hot = a < w.A0 ? (a == own_act[rr * 2]) : (a - w.A0 == own_act[rr * 2 + 1]);
+              io.onehot[env0 * N * w.A + i] = hot ? 1.0f : 0.0f;
+            }
+        }
+        TL(half, 30);
+        bar_sync_n(1, 256);  // staging (aliases x), exchange and action buffers of both tiles are free again
+        TL(half, 31);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_free(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
 static int sm_count_tc() {
@@ -719,8 +1125,27 @@ static int sm_count_tc() {
 }
 
 template <int SC, int N, bool FUSED, int APAD>
+static cudaError_t launch_tc2_t(const EnvState<float> &s, const TcDev &w, const ActorIO &io, const RolloutIO &ro,
+                                int max_episode_len, int64_t nenvs, cudaStream_t st) {
+  const size_t smem = tc2_smem_bytes(w.bytes, N, w.Kx, APAD);
+  cudaError_t e = cudaFuncSetAttribute(k_tc2<SC, N, FUSED, APAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t ntiles = (nenvs + kRows - 1) / kRows;
+  const int nsm = sm_count_tc();
+  const int64_t pairs = (ntiles + 1) / 2;
+  const int grid = (int)(pairs < nsm ? pairs : nsm);
+  k_tc2<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles, getenv("MPE_TC_TIMELINE") != nullptr);
+  return cudaGetLastError();
+}
+
+template <int SC, int N, bool FUSED, int APAD>
 static cudaError_t launch_tc_t(const EnvState<float> &s, const TcDev &w, const ActorIO &io, const RolloutIO &ro,
                                int max_episode_len, int64_t nenvs, cudaStream_t st) {
+  if constexpr (N <= 3) {
+    static const bool v1 = getenv("MPE_TC_V1") != nullptr;  // A/B switch: the two-independent-pipelines kernel
+    if (!v1 && tc2_smem_bytes(w.bytes, N, w.Kx, APAD) <= 227 * 1024)
+      return launch_tc2_t<SC, N, FUSED, APAD>(s, w, io, ro, max_episode_len, nenvs, st);
+  }
   const size_t smem = tc_smem_bytes(w.bytes, N, w.Kx);
   cudaError_t e = cudaFuncSetAttribute(k_tc<SC, N, FUSED, APAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -35,6 +35,12 @@ if which in ('all', 'rollout', 'actor'):
             actor.forward(obs)
     torch.cuda.synchronize()
 if which in ('all', 'bign'):
+    actor6 = m.FusedActor(actor_ref.init_state_dict(16, 5, 1), device=dev, seed=1)
+    env6 = m.make_env('simple_spread', n=6, num_envs=65536, batched=True, seed=1)
+    obs6 = env6.reset()
+    for _ in range(3):
+        actor6.forward(obs6)
+    torch.cuda.synchronize()
     for n, D in ((6, 16), (12, 28)):
         B = 1 << 18
         env = m.make_env('simple_spread', n=n, num_envs=B, batched=True, seed=1)
