@@ -197,13 +197,25 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// reciprocal of d >= 1 on the FMA pipe (no MUFU): bit-trick seed (<= 12 % off) + 3 Newton steps (-> ~4e-8), packed
+__device__ __forceinline__ f2 rcp2_newton(f2 d) {
+  float d0, d1;
+  upk(d, d0, d1);
+  f2 r = pk(__uint_as_float(0x7EF311C7u - __float_as_uint(d0)), __uint_as_float(0x7EF311C7u - __float_as_uint(d1)));
+  const f2 nd = mul2(d, pk(-1.0f, -1.0f)), TWO = pk(2.0f, 2.0f);
+#pragma unroll
+  for (int it = 0; it < 3; ++it) r = mul2(r, fma2(nd, r, TWO));
+  return r;
+}
+
 // LSTM cell math for 8 units of one env row.  v = 32 gate accumulator columns (scaled by 16) in the packed order
 // [i_a i_b f_a f_b g_a g_b o_a o_b] per pair of units (a, b) = (2p, 2p+1), so that the two cells of a pair sit in
 // adjacent registers and every FP32 operation of the cell is one FFMA2/FADD2/FMUL2.  bg = 32 biases in the same
 // order, pre-multiplied by -log2(e) (x2 for the g gate); c = the 4 packed cell-state pairs; pl = packed dense2
-// partial sums.  Per cell: 8 MUFU ops (5 ex2 + 3 rcp; the sigmoid*tanh products share a reciprocal):
-//   sigmoid(i) tanh(g) = (1 - eg) / ((1 + ei)(1 + eg)),  sigmoid(f) = 1 / (1 + ef),  with e* = exp(-x);
-//   ei/ef/eo may overflow to +inf (quotient 0); eg/ec are clamped so that 1 - e stays finite.
+// partial sums.  The MUFU pipe is the floor of this kernel, so the cell is arranged to need 6 MUFU ops (5 ex2 +
+// 1 rcp) instead of the textbook 10: with e* = exp(-x) (arguments clamped so that no product overflows)
+//   c' = sigmoid(f) c + sigmoid(i) tanh(g) = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ef)(1+ei)(1+eg)]   one rcp
+//   h  = sigmoid(o) tanh(c') = (1 - ec) / ((1+eo)(1+ec))          reciprocal by Newton iteration on the FMA pipe
 // Writes h as an fp16 hi/lo K-chunk of the recurrent A operand when `store_h`.
 template <int APAD>
 __device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float *bg, const float *w2rows, f2 (&c)[4],
@@ -211,9 +223,10 @@ __device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float 
   const f2 ONE = pk(1.0f, 1.0f), NEG1 = pk(-1.0f, -1.0f);
   const f2 S1 = pk(-kWInv * kLog2e, -kWInv * kLog2e), S2 = pk(-2.0f * kWInv * kLog2e, -2.0f * kWInv * kLog2e);
   const f2 S3 = pk(-2.0f * kLog2e, -2.0f * kLog2e);
+  constexpr float kClamp = 40.0f;  // e <= 2^40: sigmoid floors at 9e-13, tanh saturates to 1 - 2e-12
   float hv[8];
-  f2 pI[4], pF[4], pG[4], pO[4], nG[4];
-  // stage 1: ex2 arguments (FFMA2), exponentials (MUFU), 1 + e / 1 - e (FADD2 / FFMA2)
+  f2 pO[4];
+  // stage 1: exponentials of the four gates, then the new cell state with a single reciprocal
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(bg + p * 8);      // (b_i pair, b_f pair)
@@ -221,32 +234,27 @@ __device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float 
     const f2 aI = fma2(pk(v[8 * p + 0], v[8 * p + 1]), S1, b0.x), aF = fma2(pk(v[8 * p + 2], v[8 * p + 3]), S1, b0.y);
     const f2 aG = fma2(pk(v[8 * p + 4], v[8 * p + 5]), S2, b1.x), aO = fma2(pk(v[8 * p + 6], v[8 * p + 7]), S1, b1.y);
     float x0, x1;
-    upk(aI, x0, x1); const f2 eI = pk(ex2_approx(x0), ex2_approx(x1));
-    upk(aF, x0, x1); const f2 eF = pk(ex2_approx(x0), ex2_approx(x1));
-    upk(aG, x0, x1); const f2 eG = pk(ex2_approx(fminf(x0, 57.0f)), ex2_approx(fminf(x1, 57.0f)));
-    upk(aO, x0, x1); const f2 eO = pk(ex2_approx(x0), ex2_approx(x1));
-    pI[p] = add2(eI, ONE); pF[p] = add2(eF, ONE); pG[p] = add2(eG, ONE); pO[p] = add2(eO, ONE);
-    nG[p] = fma2(eG, NEG1, ONE);
+    upk(aI, x0, x1); const f2 eI = pk(ex2_approx(fminf(x0, kClamp)), ex2_approx(fminf(x1, kClamp)));
+    upk(aF, x0, x1); const f2 eF = pk(ex2_approx(fminf(x0, kClamp)), ex2_approx(fminf(x1, kClamp)));
+    upk(aG, x0, x1); const f2 eG = pk(ex2_approx(fminf(x0, kClamp)), ex2_approx(fminf(x1, kClamp)));
+    upk(aO, x0, x1); const f2 eO = pk(ex2_approx(fminf(x0, kClamp)), ex2_approx(fminf(x1, kClamp)));
+    const f2 F = add2(eF, ONE), P = mul2(add2(eI, ONE), add2(eG, ONE));
+    const f2 num = fma2(c[p], P, mul2(fma2(eG, NEG1, ONE), F));
+    float d0, d1;
+    upk(mul2(F, P), d0, d1);
+    c[p] = mul2(num, pk(rcp_approx(d0), rcp_approx(d1)));
+    pO[p] = add2(eO, ONE);
   }
-  // stage 2: c = sigmoid(f) c + sigmoid(i) tanh(g)
+  // stage 2: h = sigmoid(o) tanh(c) = (1 - ec) / ((1 + eo)(1 + ec)), reciprocal on the FMA pipe
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    float d0, d1, f0, f1;
-    upk(mul2(pI[p], pG[p]), d0, d1);
-    upk(pF[p], f0, f1);
-    const f2 ig = mul2(nG[p], pk(rcp_approx(d0), rcp_approx(d1)));
-    c[p] = fma2(pk(rcp_approx(f0), rcp_approx(f1)), c[p], ig);
-  }
-  // stage 3: h = sigmoid(o) tanh(c) = (1 - ec) / ((1 + eo)(1 + ec))
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    float x0, x1, d0, d1;
+    float x0, x1;
     upk(mul2(c[p], S3), x0, x1);
-    const f2 eC = pk(ex2_approx(fminf(x0, 57.0f)), ex2_approx(fminf(x1, 57.0f)));
-    upk(mul2(pO[p], add2(eC, ONE)), d0, d1);
-    upk(mul2(fma2(eC, NEG1, ONE), pk(rcp_approx(d0), rcp_approx(d1))), hv[2 * p], hv[2 * p + 1]);
+    const f2 eC = pk(ex2_approx(fminf(x0, kClamp)), ex2_approx(fminf(x1, kClamp)));
+    const f2 r = rcp2_newton(mul2(pO[p], add2(eC, ONE)));
+    upk(mul2(fma2(eC, NEG1, ONE), r), hv[2 * p], hv[2 * p + 1]);
   }
-  // stage 4: dense2 contribution of relu(h): FFMA2 over pairs of head entries, weights broadcast from smem
+  // stage 3: dense2 contribution of relu(h): FFMA2 over pairs of head entries, weights broadcast from smem
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float rj = fmaxf(hv[j], 0.0f);
@@ -893,7 +901,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&bb[B_H1]);
-            if (j < 13) TL(half, 1 + 2 * j);
           }
           if (j >= 1) {  // C(X', k'): the cell whose E1 ran one half-iteration ago
             const int X = (j - 1) & 1, k = (j - 1) >> 1, d = k / N, st = k - d * N;
@@ -912,7 +919,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int a = 0; a < APAD / 2; ++a) pl[a] = 0ull;
             mbar_wait(&bb[B_G], ph_g[X]); ph_g[X] ^= 1;
             tc_fence_after();
-            if (j < 14) TL(half, 2 * j);
             {
               uint32_t va[32], vb[32];
               tmem_ld32(tmem + lane_base + half * 64, va);
