@@ -75,6 +75,8 @@ struct MpeReplay {
   int device = 0;
   int64_t size = 0, head = 0;  // host-side ring counters (rls/replay_buffer.py: len(_storage), _next_idx)
   uint64_t draws = 0;          // Philox counter of make_index calls
+  int64_t *idx_scratch = nullptr;  // indices drawn by replay_sample when the caller passes none
+  int64_t idx_cap = 0;
 };
 
 extern "C" {
@@ -507,7 +509,7 @@ int replay_destroy(MpeReplay *r) {
   if (r == nullptr) return MPE_OK;
   DeviceGuard g(r->device);
   cudaDeviceSynchronize();
-  void *ptrs[] = {r->dev.obs, r->dev.obs_next, r->dev.act_u, r->dev.act_c, r->dev.rew, r->dev.done};
+  void *ptrs[] = {r->dev.obs, r->dev.obs_next, r->dev.act_u, r->dev.act_c, r->dev.rew, r->dev.done, r->idx_scratch};
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
   delete r;
@@ -543,8 +545,26 @@ int replay_sample(MpeReplay *r, int64_t batch, const int64_t *idx, uint64_t seed
   if (batch <= 0) return MPE_OK;
   if (r->size <= 0) return fail(MPE_EINVAL, "replay_sample: the ring is empty");
   DeviceGuard g(r->device);
-  CK(mpe::launch_replay_sample(r->dev, r->size, batch, idx, seed, r->draws, obs, act_onehot, rew, obs_next, done, idx_out,
-                               static_cast<cudaStream_t>(stream)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t *use = idx;
+  if (idx == nullptr) {  // ReplayBuffer.make_index: uniform with replacement, into idx_out or a private scratch
+    int64_t *dst = idx_out;
+    if (dst == nullptr) {
+      if (batch > r->idx_cap) {
+        if (r->idx_scratch != nullptr) cudaFree(r->idx_scratch);
+        r->idx_scratch = nullptr; r->idx_cap = 0;
+        CK(cudaMalloc(&r->idx_scratch, (size_t)batch * sizeof(int64_t)));
+        r->idx_cap = batch;
+      }
+      dst = r->idx_scratch;
+    }
+    CK(mpe::launch_replay_make_index(r->size, batch, seed, r->draws, dst, st));
+    use = dst;
+  } else if (idx_out != nullptr) {
+    CK(cudaMemcpyAsync(idx_out, idx, (size_t)batch * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  }
+  if (obs != nullptr || act_onehot != nullptr || rew != nullptr || obs_next != nullptr || done != nullptr)
+    CK(mpe::launch_replay_gather(r->dev, batch, use, obs, act_onehot, rew, obs_next, done, st));
   if (idx == nullptr) r->draws += 1;
   return MPE_OK;
 }

@@ -9,101 +9,118 @@
 
 namespace mpe {
 
+// Both kernels are element-parallel over the flattened [rows][R] observation arrays (8 B vectors when R is even), so
+// every lane moves data even though one transition is only R * 4 = 120 B (simple_spread N = 3); the per-row
+// extras (action indices, shared reward, done flag) are handled by the first threads of each row.
+
 // append B transitions at ring slots (head + b) % capacity
+template <int V>  // V = floats per vector (2 or 1)
 __global__ void __launch_bounds__(256) k_replay_add(ReplayDev r, int64_t head, int64_t B, const float *__restrict__ obs,
                                                     const int32_t *__restrict__ act_u, const int32_t *__restrict__ act_c,
                                                     const float *__restrict__ rew, const float *__restrict__ obs_next,
                                                     const float *__restrict__ done) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int R = r.N * r.D;
-  for (int64_t b = warp; b < B; b += nwarps) {
+  const int R = r.N * r.D, RV = R / V;
+  const int64_t total = B * RV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / RV;
+    const int c = (int)(i - b * RV);
     const int64_t slot = (head + b) % r.capacity;
-    const float *so = obs + b * R, *sn = obs_next + b * R;
-    float *dobs = r.obs + slot * R, *dnext = r.obs_next + slot * R;
-    if ((R & 3) == 0 && ((reinterpret_cast<uintptr_t>(so) | reinterpret_cast<uintptr_t>(sn)) & 15) == 0) {
-      for (int i = lane; i < R / 4; i += 32) {
-        reinterpret_cast<float4 *>(dobs)[i] = reinterpret_cast<const float4 *>(so)[i];
-        reinterpret_cast<float4 *>(dnext)[i] = reinterpret_cast<const float4 *>(sn)[i];
-      }
+    if (V == 2) {
+      reinterpret_cast<float2 *>(r.obs + slot * R)[c] = reinterpret_cast<const float2 *>(obs + b * R)[c];
+      reinterpret_cast<float2 *>(r.obs_next + slot * R)[c] = reinterpret_cast<const float2 *>(obs_next + b * R)[c];
     } else {
-      for (int i = lane; i < R; i += 32) { dobs[i] = so[i]; dnext[i] = sn[i]; }
+      r.obs[slot * R + c] = obs[b * R + c];
+      r.obs_next[slot * R + c] = obs_next[b * R + c];
     }
-    if (lane < r.N) {
-      r.act_u[slot * r.N + lane] = (int8_t)act_u[b * r.N + lane];
-      r.act_c[slot * r.N + lane] = act_c != nullptr ? (int8_t)act_c[b * r.N + lane] : (int8_t)0;
+    if (c < r.N) {
+      r.act_u[slot * r.N + c] = (int8_t)act_u[b * r.N + c];
+      r.act_c[slot * r.N + c] = act_c != nullptr ? (int8_t)act_c[b * r.N + c] : (int8_t)0;
     }
-    if (lane == 0) {
+    if (c == 0) {
       float s = 0.0f;  // rew_shared = np.sum(rew_n) (experiments/run.py:46), agent order
-      for (int i = 0; i < r.N; ++i) s += rew[b * r.N + i];
+      for (int n = 0; n < r.N; ++n) s += rew[b * r.N + n];
       r.rew[slot] = s;
       r.done[slot] = done != nullptr ? done[b] : 0.0f;
     }
   }
 }
 
-// gather `batch` transitions: idx given, or drawn uniformly with replacement from [0, size) by Philox
-__global__ void __launch_bounds__(256) k_replay_sample(ReplayDev r, int64_t size, int64_t batch, const int64_t *__restrict__ idx_in,
-                                                       uint64_t seed, uint64_t counter, float *__restrict__ obs,
-                                                       float *__restrict__ act_onehot, float *__restrict__ rew,
-                                                       float *__restrict__ obs_next, float *__restrict__ done,
-                                                       int64_t *__restrict__ idx_out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int R = r.N * r.D, A = r.A0 + r.A1;
-  for (int64_t j = warp; j < batch; j += nwarps) {
-    int64_t slot;
-    if (idx_in != nullptr) {
-      slot = idx_in[j];
-    } else {  // random.randint(0, len - 1) with replacement (rls/replay_buffer.py:51-52)
-      const uint4 rr = philox_raw(seed, (uint64_t)j, (uint32_t)counter, 4u, (uint32_t)(counter >> 32));
-      const uint64_t r64 = ((uint64_t)rr.x << 32) | rr.y;
-      slot = (int64_t)__umul64hi(r64, (uint64_t)size);
-    }
-    if (idx_out != nullptr && lane == 0) idx_out[j] = slot;
-    const float *so = r.obs + slot * R, *sn = r.obs_next + slot * R;
-    if ((R & 3) == 0 && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(obs_next)) & 15) == 0) {
-      for (int i = lane; i < R / 4; i += 32) {
-        if (obs != nullptr) reinterpret_cast<float4 *>(obs + j * R)[i] = reinterpret_cast<const float4 *>(so)[i];
-        if (obs_next != nullptr) reinterpret_cast<float4 *>(obs_next + j * R)[i] = reinterpret_cast<const float4 *>(sn)[i];
-      }
+// uniform indices with replacement: random.randint(0, len - 1) per sample (rls/replay_buffer.py:51-52)
+__global__ void __launch_bounds__(256) k_replay_make_index(int64_t size, int64_t batch, uint64_t seed, uint64_t counter,
+                                                           int64_t *__restrict__ idx) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < batch; j += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 rr = philox_raw(seed, (uint64_t)j, (uint32_t)counter, 4u, (uint32_t)(counter >> 32) & 0xFFFFu);
+    idx[j] = (int64_t)__umul64hi(((uint64_t)rr.x << 32) | rr.y, (uint64_t)size);
+  }
+}
+
+// gather `batch` transitions by index
+template <int V>
+__global__ void __launch_bounds__(256) k_replay_gather(ReplayDev r, int64_t batch, const int64_t *__restrict__ idx,
+                                                       float *__restrict__ obs, float *__restrict__ act_onehot,
+                                                       float *__restrict__ rew, float *__restrict__ obs_next,
+                                                       float *__restrict__ done) {
+  const int R = r.N * r.D, RV = R / V, A = r.A0 + r.A1;
+  const int64_t total = batch * RV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / RV;
+    const int c = (int)(i - j * RV);
+    const int64_t slot = idx[j];
+    if (V == 2) {
+      if (obs != nullptr) reinterpret_cast<float2 *>(obs + j * R)[c] = reinterpret_cast<const float2 *>(r.obs + slot * R)[c];
+      if (obs_next != nullptr)
+        reinterpret_cast<float2 *>(obs_next + j * R)[c] = reinterpret_cast<const float2 *>(r.obs_next + slot * R)[c];
     } else {
-      for (int i = lane; i < R; i += 32) {
-        if (obs != nullptr) obs[j * R + i] = so[i];
-        if (obs_next != nullptr) obs_next[j * R + i] = sn[i];
-      }
+      if (obs != nullptr) obs[j * R + c] = r.obs[slot * R + c];
+      if (obs_next != nullptr) obs_next[j * R + c] = r.obs_next[slot * R + c];
     }
     if (act_onehot != nullptr)
-      for (int i = lane; i < r.N * A; i += 32) {
-        const int n = i / A, a = i - n * A;
-        const int u = r.act_u[slot * r.N + n], c = r.act_c[slot * r.N + n];
-        act_onehot[j * r.N * A + i] = (a < r.A0 ? a == u : a - r.A0 == c) ? 1.0f : 0.0f;
+      for (int e = c; e < r.N * A; e += RV) {
+        const int n = e / A, a = e - n * A;
+        const int u = r.act_u[slot * r.N + n], cc = r.act_c[slot * r.N + n];
+        act_onehot[j * r.N * A + e] = (a < r.A0 ? a == u : a - r.A0 == cc) ? 1.0f : 0.0f;
       }
-    if (lane == 0) {
+    if (c == 0) {
       if (rew != nullptr) rew[j] = r.rew[slot];
       if (done != nullptr) done[j] = r.done[slot];
     }
   }
 }
 
+static unsigned grid_for(int64_t total) {
+  const int64_t blocks = (total + 255) / 256;
+  return (unsigned)(blocks < 148 * 32 ? (blocks > 0 ? blocks : 1) : 148 * 32);
+}
+
 cudaError_t launch_replay_add(const ReplayDev &r, int64_t head, int64_t B, const float *obs, const int32_t *act_u,
                               const int32_t *act_c, const float *rew, const float *obs_next, const float *done,
                               cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  const int64_t blocks = (B + 7) / 8;  // 8 warps per block, one transition per warp
-  k_replay_add<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(r, head, B, obs, act_u, act_c, rew, obs_next, done);
+  const int R = r.N * r.D;
+  const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(obs_next)) & 7) == 0;
+  if (v2)
+    k_replay_add<2><<<grid_for(B * (R / 2)), 256, 0, st>>>(r, head, B, obs, act_u, act_c, rew, obs_next, done);
+  else
+    k_replay_add<1><<<grid_for(B * R), 256, 0, st>>>(r, head, B, obs, act_u, act_c, rew, obs_next, done);
   return cudaGetLastError();
 }
 
-cudaError_t launch_replay_sample(const ReplayDev &r, int64_t size, int64_t batch, const int64_t *idx_in, uint64_t seed,
-                                 uint64_t counter, float *obs, float *act_onehot, float *rew, float *obs_next, float *done,
-                                 int64_t *idx_out, cudaStream_t st) {
+cudaError_t launch_replay_make_index(int64_t size, int64_t batch, uint64_t seed, uint64_t counter, int64_t *idx,
+                                     cudaStream_t st) {
   if (batch <= 0) return cudaSuccess;
-  const int64_t blocks = (batch + 7) / 8;
-  k_replay_sample<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(r, size, batch, idx_in, seed, counter, obs,
-                                                                                     act_onehot, rew, obs_next, done, idx_out);
+  k_replay_make_index<<<grid_for(batch), 256, 0, st>>>(size, batch, seed, counter, idx);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_replay_gather(const ReplayDev &r, int64_t batch, const int64_t *idx, float *obs, float *act_onehot,
+                                 float *rew, float *obs_next, float *done, cudaStream_t st) {
+  if (batch <= 0) return cudaSuccess;
+  const int R = r.N * r.D;
+  const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(obs_next)) & 7) == 0;
+  if (v2)
+    k_replay_gather<2><<<grid_for(batch * (R / 2)), 256, 0, st>>>(r, batch, idx, obs, act_onehot, rew, obs_next, done);
+  else
+    k_replay_gather<1><<<grid_for(batch * R), 256, 0, st>>>(r, batch, idx, obs, act_onehot, rew, obs_next, done);
   return cudaGetLastError();
 }
 

@@ -16,8 +16,9 @@ struct ReplayDev {
 cudaError_t launch_replay_add(const ReplayDev &r, int64_t head, int64_t B, const float *obs, const int32_t *act_u,
                               const int32_t *act_c, const float *rew, const float *obs_next, const float *done,
                               cudaStream_t st);
-cudaError_t launch_replay_sample(const ReplayDev &r, int64_t size, int64_t batch, const int64_t *idx_in, uint64_t seed,
-                                 uint64_t counter, float *obs, float *act_onehot, float *rew, float *obs_next, float *done,
-                                 int64_t *idx_out, cudaStream_t st);
+cudaError_t launch_replay_make_index(int64_t size, int64_t batch, uint64_t seed, uint64_t counter, int64_t *idx,
+                                     cudaStream_t st);
+cudaError_t launch_replay_gather(const ReplayDev &r, int64_t batch, const int64_t *idx, float *obs, float *act_onehot,
+                                 float *rew, float *obs_next, float *done, cudaStream_t st);
 
 }  // namespace mpe

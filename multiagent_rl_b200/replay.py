@@ -74,7 +74,10 @@ class DeviceReplayBuffer(object):
 
     def make_index(self, batch_size):
         """Uniform indices with replacement (``random.randint(0, len - 1)`` per sample), on the device."""
-        _, idx = self._gather(int(batch_size), None)
+        batch = int(batch_size)
+        idx = torch.empty((batch,), dtype=torch.int64, device=self.device)
+        _lib.check(self._lib.replay_sample(self._h, batch, None, C.c_uint64(self.seed), None, None, None, None, None,
+                                           _lib.ptr(idx), _lib.current_stream(self.device)), 'replay_sample')
         return idx
 
     def make_latest_index(self, batch_size):
