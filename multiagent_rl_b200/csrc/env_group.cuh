@@ -35,6 +35,85 @@ struct GroupLayout {
   static_assert(N % G == 0, "agents must split evenly over the lanes of an env");
 };
 
+// lane bookkeeping of the lanes-per-env kernels
+template <typename T, int N, int G>
+struct GroupLanes {
+  int warp, lane, el, q, base_lane;
+  int64_t b0, b;
+  bool lane_ok, active, full;
+};
+
+// Observation rows of the lane's own agents (+ optional rewards) -> caller-facing obs[b][N][D] / rew[b][N]; a warp's
+// envs are one contiguous span of both, staged in shared memory and handed to the TMA engine.  Returns whether this
+// lane issued bulk stores (it must then call bulk_wait_read_all() before the kernel ends).
+template <typename T, int N, int G>
+__device__ __forceinline__ bool grp_emit(const GroupLanes<T, N, G> &g, const T (&px)[N / G], const T (&py)[N / G],
+                                         const T (&vx)[N / G], const T (&vy)[N / G], const T (&lx)[N / G],
+                                         const T (&ly)[N / G], const T *r, T *obs, T *rew, unsigned char *smem) {
+  using GL = GroupLayout<T, N, G>;
+  constexpr int A = GL::A, EPW = GL::EPW, D = GL::D, R = GL::R, L = N;
+  const unsigned FULL = 0xffffffffu;
+  const int warp = g.warp, lane = g.lane, el = g.el, q = g.q, base_lane = g.base_lane;
+  const int64_t b0 = g.b0, b = g.b;
+  const bool lane_ok = g.lane_ok, active = g.active, full = g.full;
+  constexpr int RS = GL::RS;
+  T *st_obs = reinterpret_cast<T *>(smem + warp * GL::kWarpBytes);
+  T *st_rew = st_obs + EPW * RS;
+  const bool obs_tma = full && obs != nullptr && (reinterpret_cast<uintptr_t>(obs + b0 * R) & 15) == 0 &&
+                       (GL::kPerEnv || (EPW * R * sizeof(T)) % 16 == 0);
+  const bool rew_tma = full && rew != nullptr && (reinterpret_cast<uintptr_t>(rew + b0 * N) & 15) == 0 &&
+                       ((EPW * N * sizeof(T)) % 16 == 0);
+  if (obs != nullptr) {
+    T *rowbase = obs_tma ? st_obs + el * RS : obs + b * R;
+    const bool wr = obs_tma ? lane_ok : active;
+    if (wr) {
+#pragma unroll
+      for (int k = 0; k < A; ++k) {
+        T *row = rowbase + (q * A + k) * D;
+        row[0] = vx[k]; row[1] = vy[k]; row[2] = px[k]; row[3] = py[k];
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const T llx = __shfl_sync(FULL, lx[l % A], base_lane + l / A);
+      const T lly = __shfl_sync(FULL, ly[l % A], base_lane + l / A);
+      if (wr) {
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          T *row = rowbase + (q * A + k) * D;
+          row[4 + 2 * l] = llx - px[k];
+          row[5 + 2 * l] = lly - py[k];
+        }
+      }
+    }
+  }
+  if (rew != nullptr && (rew_tma ? lane_ok : active)) {
+    T *rr = rew_tma ? st_rew + el * N : rew + b * N;
+#pragma unroll
+    for (int k = 0; k < A; ++k) rr[q * A + k] = r[k];
+  }
+  bool issued = false;
+  if (obs_tma || rew_tma) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (GL::kPerEnv) {
+      if (obs_tma && lane_ok && q == 0) {  // one bulk store per env (rows are padded apart in smem)
+        bulk_store(obs + b * R, st_obs + el * RS, R * sizeof(T));
+        issued = true;
+      }
+    } else if (obs_tma && lane == 0) {
+      bulk_store(obs + b0 * R, st_obs, EPW * R * sizeof(T));
+      issued = true;
+    }
+    if (rew_tma && lane == 0) {
+      bulk_store(rew + b0 * N, st_rew, EPW * N * sizeof(T));
+      issued = true;
+    }
+    if (issued) bulk_commit();
+  }
+  return issued;
+}
+
 template <typename T, int N, int G>
 __global__ void __launch_bounds__(kStepThreads)
     k_step_grp(EnvState<T> s, const int32_t *__restrict__ act_u, T *__restrict__ obs, T *__restrict__ rew,
@@ -162,65 +241,79 @@ __global__ void __launch_bounds__(kStepThreads)
     if (info_f != nullptr && q == 0) info_f[b] = md;
   }
 
-  // ---- outputs: rows of the lane's own agents; a warp's envs are one contiguous span of obs / rew ----
-  constexpr int RS = GL::RS;
-  T *st_obs = reinterpret_cast<T *>(smem + warp * GL::kWarpBytes);
-  T *st_rew = st_obs + EPW * RS;
-  const bool obs_tma = full && obs != nullptr && (reinterpret_cast<uintptr_t>(obs + b0 * R) & 15) == 0 &&
-                       (GL::kPerEnv || (EPW * R * sizeof(T)) % 16 == 0);
-  const bool rew_tma = full && rew != nullptr && (reinterpret_cast<uintptr_t>(rew + b0 * N) & 15) == 0 &&
-                       ((EPW * N * sizeof(T)) % 16 == 0);
-  if (obs != nullptr) {
-    T *rowbase = obs_tma ? st_obs + el * RS : obs + b * R;
-    const bool wr = obs_tma ? lane_ok : active;
-    if (wr) {
-#pragma unroll
-      for (int k = 0; k < A; ++k) {
-        T *row = rowbase + (q * A + k) * D;
-        row[0] = vx[k]; row[1] = vy[k]; row[2] = px[k]; row[3] = py[k];
-      }
-    }
-#pragma unroll
-    for (int l = 0; l < L; ++l) {
-      const T llx = __shfl_sync(FULL, lx[l % A], base_lane + l / A);
-      const T lly = __shfl_sync(FULL, ly[l % A], base_lane + l / A);
-      if (wr) {
-#pragma unroll
-        for (int k = 0; k < A; ++k) {
-          T *row = rowbase + (q * A + k) * D;
-          row[4 + 2 * l] = llx - px[k];
-          row[5 + 2 * l] = lly - py[k];
-        }
-      }
-    }
-  }
-  if (rew != nullptr && (rew_tma ? lane_ok : active)) {
-    T *rr = rew_tma ? st_rew + el * N : rew + b * N;
-#pragma unroll
-    for (int k = 0; k < A; ++k) rr[q * A + k] = r[k];
-  }
-  bool issued = false;
-  if (obs_tma || rew_tma) {
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (GL::kPerEnv) {
-      if (obs_tma && lane_ok && q == 0) {  // one bulk store per env (rows are padded apart in smem)
-        bulk_store(obs + b * R, st_obs + el * RS, R * sizeof(T));
-        issued = true;
-      }
-    } else if (obs_tma && lane == 0) {
-      bulk_store(obs + b0 * R, st_obs, EPW * R * sizeof(T));
-      issued = true;
-    }
-    if (rew_tma && lane == 0) {
-      bulk_store(rew + b0 * N, st_rew, EPW * N * sizeof(T));
-      issued = true;
-    }
-    if (issued) bulk_commit();
-  }
+  GroupLanes<T, N, G> gl{warp, lane, el, q, base_lane, b0, b, lane_ok, active, full};
+  const bool issued = grp_emit<T, N, G>(gl, px, py, vx, vy, lx, ly, r, obs, rew, smem);
   if (done != nullptr && active) {
 #pragma unroll
     for (int k = 0; k < A; ++k) done[b * N + q * A + k] = 0;
+  }
+  if (issued) bulk_wait_read_all();
+}
+
+// env.reset() / scenario.observation for the same lane layout: Philox reset of the masked (or timed-out) envs, then
+// the observation rows of every env.  Same draws as Env::reset (entities in upstream's order: agents, landmarks).
+template <typename T, int N, int G>
+__global__ void __launch_bounds__(kStepThreads)
+    k_reset_grp(EnvState<T> s, const uint8_t *__restrict__ mask, T *__restrict__ obs, int auto_len, int do_reset) {
+  using GL = GroupLayout<T, N, G>;
+  constexpr int A = GL::A, EPW = GL::EPW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int el = lane / G, q = lane - el * G;
+  const int base_lane = el * G;
+  const int64_t b0 = ((int64_t)blockIdx.x * (kStepThreads / 32) + warp) * EPW;
+  const int64_t b = b0 + el;
+  const bool lane_ok = lane < GL::LANES;
+  const bool active = lane_ok && b < s.B;
+  const bool full = b0 + EPW <= s.B;
+  T px[A], py[A], vx[A], vy[A], lx[A], ly[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) px[k] = py[k] = vx[k] = vy[k] = lx[k] = ly[k] = (T)0;
+  double ret = 0.0, n_ep = 0.0, n_steps = 0.0;
+  uint32_t ep_old = 0;
+  int t_old = 0;
+  bool doit = false;
+  if (active) {  // every lane of an env reads the counters before lane 0 of the env rewrites them below
+    ep_old = s.episode[b];
+    t_old = s.tstep[b];
+    doit = do_reset && (mask == nullptr || mask[b] != 0) && (auto_len <= 0 || t_old >= auto_len);
+  }
+  __syncwarp();
+  if (active) {
+    if (doit) {
+      const uint32_t ep = ep_old + 1u;
+      const uint64_t gid = (uint64_t)(s.gid0 + b);
+#pragma unroll
+      for (int k = 0; k < A; ++k) {
+        const int ia = q * A + k, il = N + q * A + k;  // entity indices of the lane's k-th agent / landmark
+        const uint4 ra = philox_raw(s.seed, gid, ep, kDomainReset, ia >> 1);
+        px[k] = bits_to_pos<T>((ia & 1) ? ra.z : ra.x); py[k] = bits_to_pos<T>((ia & 1) ? ra.w : ra.y);
+        const uint4 rl = philox_raw(s.seed, gid, ep, kDomainReset, il >> 1);
+        lx[k] = bits_to_pos<T>((il & 1) ? rl.z : rl.x); ly[k] = bits_to_pos<T>((il & 1) ? rl.w : rl.y);
+        st4(s.pv + ((int64_t)ia * s.B + b) * 4, Vec4<T>{px[k], py[k], (T)0, (T)0});
+        st2(s.lm + ((int64_t)(q * A + k) * s.B + b) * 2, Vec2<T>{lx[k], ly[k]});
+      }
+      if (q == 0) {
+        if (s.track && t_old > 0) { ret = (double)s.ep_ret[b]; n_ep = 1.0; n_steps = (double)t_old; }
+        s.episode[b] = ep;
+        s.tstep[b] = 0;
+        s.ep_ret[b] = (T)0;
+      }
+    } else if (obs != nullptr) {
+#pragma unroll
+      for (int k = 0; k < A; ++k) {
+        const Vec4<T> v = ld4(s.pv + ((int64_t)(q * A + k) * s.B + b) * 4);
+        px[k] = v.x; py[k] = v.y; vx[k] = v.z; vy[k] = v.w;
+        const Vec2<T> l = ld2(s.lm + ((int64_t)(q * A + k) * s.B + b) * 2);
+        lx[k] = l.x; ly[k] = l.y;
+      }
+    }
+  }
+  if (s.track && do_reset) fold_stats(s.stats, ret, n_ep, n_steps);
+  bool issued = false;
+  if (obs != nullptr) {
+    GroupLanes<T, N, G> gl{warp, lane, el, q, base_lane, b0, b, lane_ok, active, full};
+    issued = grp_emit<T, N, G>(gl, px, py, vx, vy, lx, ly, nullptr, obs, nullptr, smem);
   }
   if (issued) bulk_wait_read_all();
 }

@@ -346,9 +346,26 @@ inline cudaError_t set_smem(K kernel, int bytes) {
   return cudaSuccess;
 }
 
+#define MPE_GRP_RESET(NN, GG, DO_RESET)                                                                            \
+  {                                                                                                                \
+    using GL = GroupLayout<T, NN, GG>;                                                                             \
+    constexpr int sm = GL::kBlockBytes;                                                                            \
+    cudaError_t err = set_smem<T>(k_reset_grp<T, NN, GG>, sm);                                                     \
+    if (err != cudaSuccess) return err;                                                                            \
+    const int64_t per_block = (int64_t)GL::EPW * (kStepThreads / 32);                                              \
+    k_reset_grp<T, NN, GG><<<(unsigned)((a.B + per_block - 1) / per_block), kStepThreads, sm, st>>>(               \
+        typed<T>(a), mask, static_cast<T *>(obs), auto_len, DO_RESET);                                             \
+    return cudaGetLastError();                                                                                     \
+  }
+
 template <typename T>
 cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
+  if (a.scenario == kSpread && (a.N == 6 || a.N == 9 || a.N == 12)) {  // G lanes per env (env_group.cuh)
+    if (a.N == 6) MPE_GRP_RESET(6, 2, 1)
+    if (a.N == 9) MPE_GRP_RESET(9, 3, 1)
+    MPE_GRP_RESET(12, 4, 1)
+  }
   const unsigned grid = (unsigned)((a.B + kStepThreads - 1) / kStepThreads);
 #define CALL(SC, NN)                                                                          \
   {                                                                                           \
@@ -365,6 +382,13 @@ cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs,
 template <typename T>
 cudaError_t launch_observe_t(const EnvStateAny &a, void *obs, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
+  if (a.scenario == kSpread && (a.N == 6 || a.N == 9 || a.N == 12)) {
+    const uint8_t *mask = nullptr;
+    const int auto_len = 0;
+    if (a.N == 6) MPE_GRP_RESET(6, 2, 0)
+    if (a.N == 9) MPE_GRP_RESET(9, 3, 0)
+    MPE_GRP_RESET(12, 4, 0)
+  }
   const unsigned grid = (unsigned)((a.B + kStepThreads - 1) / kStepThreads);
 #define CALL(SC, NN)                                                                    \
   {                                                                                     \
