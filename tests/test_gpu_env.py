@@ -73,7 +73,8 @@ def test_golden_trajectories(golden_dir, scenario, n, precision):
 
 
 @pytest.mark.parametrize('precision', ['fp64', 'fp32'])
-@pytest.mark.parametrize('scenario,n', [('simple_spread', None), ('simple_spread', 6), ('simple_reference', None),
+@pytest.mark.parametrize('scenario,n', [('simple_spread', None), ('simple_spread', 6), ('simple_spread', 9),
+                                        ('simple_spread', 12), ('simple_reference', None),
                                         ('simple_speaker_listener', None)])
 def test_philox_reset_is_bit_exact(scenario, n, precision):
     B, off, seed = 1000, 12345, 12345678
