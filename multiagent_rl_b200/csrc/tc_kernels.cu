@@ -739,6 +739,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     k_tc2(EnvState<float> s, TcDev w, ActorIO io, RolloutIO ro, int max_episode_len, int64_t ntiles, int dbg) {
   static_assert(N <= 3, "k_tc2 keeps all obs operands resident");
   extern __shared__ __align__(128) unsigned char smem[];
+  const int skew = dbg >> 8;  // experiment: warpgroup 1 enters the cell pipeline this many cycles late
+  dbg &= 1;
+  if (dbg && threadIdx.x == 0 && blockIdx.x < 148) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_tc_timeline[blockIdx.x * 128 + 64] = gt;
+    g_tc_timeline[blockIdx.x * 128 + 66] = clock64();
+  }
   using Dm = Dims<SC, N>;
   const int D = FUSED ? Dm::D : w.D;
   const int R = N * D;
@@ -822,11 +830,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const float *w2f = reinterpret_cast<const float *>(sm_w + w.off_w2f);
     unsigned char *own_x = tile_smem(own), *own_h = own_x + xb;
     uint8_t *own_act = own_h + 16384;
-    float *own_xchg = reinterpret_cast<float *>(own_act + (kRows * N * 2 + 127) / 128 * 128);
+    const f2 *own_xchg2 = reinterpret_cast<const f2 *>(own_act + (kRows * N * 2 + 127) / 128 * 128);
     float *stage_obs = reinterpret_cast<float *>(own_x), *stage_rew = stage_obs + kRows * R;
     uint32_t ph_d1[2] = {0, 0}, ph_g[2] = {0, 0};
     mbar_wait(&bars[0], 0);
+    if (dbg && tid == 0 && blockIdx.x < 148) g_tc_timeline[blockIdx.x * 128 + 67] = clock64();
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      if (dbg && tid == 0 && blockIdx.x < 148 && pair != blockIdx.x) g_tc_timeline[blockIdx.x * 128 + 68] = clock64();
       const int64_t tile = pair * 2 + own;                 // the tile this warpgroup owns (may not exist)
       const int64_t env0 = tile * kRows;
       const int64_t nb = FUSED ? s.B : io.B;
@@ -876,91 +886,129 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         fence_proxy_async_smem();
         mbar_arrive(&bars[1 + own * B_PER_WG + B_X]);
 
-        float lg[N][APAD];  // dense2 sums of the OWN tile's rows over this thread's 16 units (+ bias)
+        // dense2 sums of the OWN tile's rows over this thread's 16 units (+ bias), packed pairs of head entries
+        f2 lgp[N][APAD / 2];
 #pragma unroll
         for (int t = 0; t < N; ++t)
 #pragma unroll
-          for (int a = 0; a < APAD; ++a) lg[t][a] = b2[a];
+          for (int a = 0; a < APAD / 2; ++a) lgp[t][a] = pk(b2[2 * a], b2[2 * a + 1]);
 
-        // cell state of this thread's 16 units (2 chunks x 4 packed pairs) for the two tiles; cP belongs to the tile
-        // whose cell is computed in the current half-iteration, the two swap every half-iteration
-        f2 cP[2][4], cQ[2][4];
-        // ---- the interleaved cell pipeline: half-iteration j = (tile X = j & 1, cell k = j >> 1) ----
-#pragma unroll 1
-        for (int j = 0; j <= 4 * N; ++j) {
-          if (j < 4 * N) {  // E1(X, k): dense1 epilogue of this thread's 32 hidden columns
-            const int X = j & 1;
-            uint64_t *bb = bars + 1 + X * B_PER_WG;
-            const uint32_t tmem = tmem_base + X * 256;
-            mbar_wait(&bb[B_D1], ph_d1[X]); ph_d1[X] ^= 1;
-            tc_fence_after();
-            uint32_t v0[32];
-            tmem_ld32(tmem + lane_base + col_d1 + half * 32, v0);
+        // cell state of this thread's 16 units (2 chunks x 4 packed pairs), one set per tile
+        f2 cA[2][4], cB[2][4];
+#ifdef MPE_TC_PHASES  // per-phase cycle accounting of the pipeline (tools/tc_timeline.py); costs ~12 registers
+        uint32_t acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock();
+#define TS(i)                                   \
+  do {                                          \
+    if (dbg) {                                  \
+      const uint32_t now = clock();             \
+      acc[i] += now - tlast;                    \
+      tlast = now;                              \
+    }                                           \
+  } while (0)
+#else
+#define TS(i)
+#endif
+        // E1(X): dense1 epilogue of this thread's 32 hidden columns of tile X's next cell
+        auto E1 = [&](auto XT) {
+          constexpr int X = decltype(XT)::value;
+          uint64_t *bb = bars + 1 + X * B_PER_WG;
+          const uint32_t tmem = tmem_base + X * 256;
+          TS(9);
+          mbar_wait(&bb[B_D1], ph_d1[X]); ph_d1[X] ^= 1;
+          tc_fence_after();
+          TS(0);
+          uint32_t v0[32];
+          tmem_ld32(tmem + lane_base + col_d1 + half * 32, v0);
+          tmem_wait_ld();
+          TS(1);
+          dense1_half(v0, b1 + half * 32, tmem + lane_base + col_h1 + half * 16);
+          TS(2);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bb[B_H1]);
+          TS(3);
+        };
+        // C(X, k): LSTM cell k of tile X on this thread's 16 units; dense2 share to lgp (own tile) or the exchange
+        auto CC = [&](auto XT, int k, f2 (&c)[2][4]) {
+          constexpr int X = decltype(XT)::value;
+          const int d = k >= N ? 1 : 0, st = k - d * N;
+          const int t = d == 0 ? st : N - 1 - st;
+          uint64_t *bb = bars + 1 + X * B_PER_WG;
+          const uint32_t tmem = tmem_base + X * 256;
+          unsigned char *sm_h = tile_smem(X) + xb;
+          if (st == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[0][q] = c[1][q] = 0ull;
+          }
+          const float *bg = reinterpret_cast<const float *>(sm_w + w.off_bg) + d * kGateN + half * 64;
+          const float *w2d = w2f + (d * kH + half * 16) * 16;
+          f2 pl[APAD / 2];
+#pragma unroll
+          for (int a = 0; a < APAD / 2; ++a) pl[a] = 0ull;
+          TS(9);
+          mbar_wait(&bb[B_G], ph_g[X]); ph_g[X] ^= 1;
+          tc_fence_after();
+          TS(4);
+          {
+            uint32_t va[32], vb[32];
+            tmem_ld32(tmem + lane_base + half * 64, va);
             tmem_wait_ld();
-            dense1_half(v0, b1 + half * 32, tmem + lane_base + col_h1 + half * 16);
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(&bb[B_H1]);
+            TS(5);
+            tmem_ld32(tmem + lane_base + half * 64 + 32, vb);  // in flight during the first chunk's math
+            lstm_chunk<APAD>(va, bg, w2d, c[0], pl, sm_h + (2 * half) * kChunkA, row, st < N - 1);
+            TS(6);
+            tmem_wait_ld();
+            TS(7);
+            lstm_chunk<APAD>(vb, bg + 32, w2d + 8 * 16, c[1], pl, sm_h + (2 * half + 1) * kChunkA, row, st < N - 1);
           }
-          if (j >= 1) {  // C(X', k'): the cell whose E1 ran one half-iteration ago
-            const int X = (j - 1) & 1, k = (j - 1) >> 1, d = k / N, st = k - d * N;
-            const int t = d == 0 ? st : N - 1 - st;
-            uint64_t *bb = bars + 1 + X * B_PER_WG;
-            const uint32_t tmem = tmem_base + X * 256;
-            unsigned char *sm_h = tile_smem(X) + xb;
-            if (st == 0) {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(&bb[B_H]);
+          TS(8);
+          if (X == own) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) cP[0][q] = cP[1][q] = 0ull;
-            }
-            const float *bg = reinterpret_cast<const float *>(sm_w + w.off_bg) + d * kGateN + half * 64;
-            const float *w2d = w2f + (d * kH + half * 16) * 16;
-            f2 pl[APAD / 2];
+            for (int tt = 0; tt < N; ++tt)
+              if (tt == t) {
 #pragma unroll
-            for (int a = 0; a < APAD / 2; ++a) pl[a] = 0ull;
-            mbar_wait(&bb[B_G], ph_g[X]); ph_g[X] ^= 1;
-            tc_fence_after();
-            {
-              uint32_t va[32], vb[32];
-              tmem_ld32(tmem + lane_base + half * 64, va);
-              tmem_wait_ld();
-              tmem_ld32(tmem + lane_base + half * 64 + 32, vb);  // in flight during the first chunk's math
-              lstm_chunk<APAD>(va, bg, w2d, cP[0], pl, sm_h + (2 * half) * kChunkA, row, st < N - 1);
-              tmem_wait_ld();
-              lstm_chunk<APAD>(vb, bg + 32, w2d + 8 * 16, cP[1], pl, sm_h + (2 * half + 1) * kChunkA, row, st < N - 1);
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(&bb[B_H]);
-            float p[APAD];
-#pragma unroll
-            for (int a = 0; a < APAD / 2; ++a) upk(pl[a], p[2 * a], p[2 * a + 1]);
-            if (X == own) {
-#pragma unroll
-              for (int tt = 0; tt < N; ++tt)
-                if (tt == t) {
-#pragma unroll
-                  for (int a = 0; a < APAD; ++a) lg[tt][a] += p[a];
-                }
-            } else {  // the other tile's rows: park this warpgroup's share for its owner (store, then add)
-              float *xr = reinterpret_cast<float *>(tile_smem(X) + xb + 16384 + (kRows * N * 2 + 127) / 128 * 128) +
-                          (size_t)t * APAD * kRows + row;
-              if (d == 0) {
-#pragma unroll
-                for (int a = 0; a < APAD; ++a) xr[a * kRows] = p[a];
-              } else {
-#pragma unroll
-                for (int a = 0; a < APAD; ++a) xr[a * kRows] += p[a];
+                for (int a = 0; a < APAD / 2; ++a) lgp[tt][a] = add2(lgp[tt][a], pl[a]);
               }
+          } else {  // the other tile's rows: park this warpgroup's share for its owner (store, then add)
+            f2 *xr = reinterpret_cast<f2 *>(tile_smem(X) + xb + 16384 + (kRows * N * 2 + 127) / 128 * 128) +
+                     (size_t)t * (APAD / 2) * kRows + row;
+            if (d == 0) {
+#pragma unroll
+              for (int a = 0; a < APAD / 2; ++a) xr[a * kRows] = pl[a];
+            } else {
+#pragma unroll
+              for (int a = 0; a < APAD / 2; ++a) xr[a * kRows] = add2(xr[a * kRows], pl[a]);
             }
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {  // swap the two tiles' cell states
-            const f2 t0 = cP[0][q], t1 = cP[1][q];
-            cP[0][q] = cQ[0][q]; cP[1][q] = cQ[1][q];
-            cQ[0][q] = t0; cQ[1][q] = t1;
-          }
+        };
+        if (skew > 0 && half == 1) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < skew) {}
+        }
+        // ---- the interleaved cell pipeline:  E1(A,0) | E1(B,k) C(A,k) E1(A,k+1) C(B,k) | ...  (tile A = 0, B = 1) ----
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        TL(half, 1);
+        E1(I0{});
+#pragma unroll 1
+        for (int k = 0; k < 2 * N; ++k) {
+          TL(half, 2 + 2 * k);
+          E1(I1{});
+          CC(I0{}, k, cA);
+          TL(half, 3 + 2 * k);
+          if (k + 1 < 2 * N) E1(I0{});
+          CC(I1{}, k, cB);
         }
         TL(half, 28);
+#ifdef MPE_TC_PHASES
+        if (dbg && first_tile) {
+#pragma unroll
+          for (int i = 0; i < 10; ++i) g_tc_timeline[blockIdx.x * 128 + 96 + half * 10 + i] = acc[i];
+        }
+#endif
         bar_sync_n(1, 256);  // the exchange buffers are complete
 
         // ---- own tile: Gumbel-max sampling ----
@@ -972,12 +1020,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
           for (int t = 0; t < N; ++t) {
             float z[APAD];
+            float lgt[APAD];
 #pragma unroll
-            for (int a = 0; a < APAD; ++a) lg[t][a] += own_xchg[((size_t)t * APAD + a) * kRows + row];
+            for (int a = 0; a < APAD / 2; ++a)
+              upk(add2(lgp[t][a], own_xchg2[((size_t)t * (APAD / 2) + a) * kRows + row]), lgt[2 * a], lgt[2 * a + 1]);
             const int64_t orow = b * N + t;
             if (!FUSED && io.gumbel != nullptr) {
 #pragma unroll
-              for (int a = 0; a < APAD; ++a) z[a] = (a < w.A && mine) ? lg[t][a] + io.gumbel[orow * w.A + a] : lg[t][a];
+              for (int a = 0; a < APAD; ++a) z[a] = (a < w.A && mine) ? lgt[a] + io.gumbel[orow * w.A + a] : lgt[a];
             } else {
 #pragma unroll
               for (int jj = 0; jj < APAD / 4; ++jj) {
@@ -989,7 +1039,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                  z[4 * jj + q] = (4 * jj + q < w.A) ? lg[t][4 * jj + q] + bits_to_gumbel(bits[q]) : 0.0f;
+                  z[4 * jj + q] = (4 * jj + q < w.A) ? lgt[4 * jj + q] + bits_to_gumbel(bits[q]) : 0.0f;
               }
             }
             int bu = 0, bc = 0;
@@ -1009,11 +1059,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (!FUSED && mine && io.logits != nullptr) {
 #pragma unroll
               for (int a = 0; a < APAD; ++a)
-                if (a < w.A) io.logits[orow * w.A + a] = lg[t][a];
+                if (a < w.A) io.logits[orow * w.A + a] = lgt[a];
             }
           }
         }
 
+        TL(half, 29);
         if (FUSED) {
           // ---- own tile: World.step + reward + outputs for env row `row` ----
           const int64_t toff = (int64_t)it * s.B;
@@ -1118,6 +1169,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_free(tmem_base, 512);
+  if (dbg && threadIdx.x == 0 && blockIdx.x < 148) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_tc_timeline[blockIdx.x * 128 + 65] = gt;
+    g_tc_timeline[blockIdx.x * 128 + 69] = clock64();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1140,7 +1197,9 @@ static cudaError_t launch_tc2_t(const EnvState<float> &s, const TcDev &w, const 
   const int nsm = sm_count_tc();
   const int64_t pairs = (ntiles + 1) / 2;
   const int grid = (int)(pairs < nsm ? pairs : nsm);
-  k_tc2<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles, getenv("MPE_TC_TIMELINE") != nullptr);
+  k_tc2<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles,
+                                                           (getenv("MPE_TC_TIMELINE") != nullptr ? 1 : 0) |
+                                                               (getenv("MPE_TC_SKEW") ? atoi(getenv("MPE_TC_SKEW")) << 8 : 0));
   return cudaGetLastError();
 }
 

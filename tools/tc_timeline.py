@@ -30,3 +30,22 @@ for cta in (0, 77):
     for role in range(4):
         v = a[cta, role]
         print(names[role], ' '.join('%d:%d' % (i, v[i] - t0) for i in range(32) if v[i] > 0))
+
+# whole-kernel view (k_tc2): globaltimer at entry / exit of every CTA, clock64 at entry, after the weight load,
+# at the start of the CTA's second tile pair, at exit
+g0, g1 = a[:, 2, 0], a[:, 2, 1]
+ok = g0 > 0
+print('kernel span over CTAs: %.1f us (first entry -> last exit); entry spread %.1f us' %
+      ((g1[ok].max() - g0[ok].min()) / 1e3, (g0[ok].max() - g0[ok].min()) / 1e3))
+c = a[:, 2, 2:6]
+for cta in (0, 39, 40, 77, 107, 108, 147):
+    e, wl, p2, x = c[cta]
+    print('CTA %3d: weights ready +%d, second pair at %s, exit +%d cycles; wall %.1f us' %
+          (cta, wl - e, ('+%d' % (p2 - e)) if p2 > 0 else '-', x - e, (g1[cta] - g0[cta]) / 1e3))
+
+names = ['wait D1', 'ld d1', 'E1 math+st issue', 'wait st+arrive', 'wait G', 'ld va', 'chunk A', 'wait vb', 'chunk B+arrive', 'other']
+for cta in (0, 77):
+    for h in range(2):
+        v = a[cta, 3, h * 10:h * 10 + 10]
+        print('CTA %d WG%d phase cycles summed over the 13 half-iterations: ' % (cta, h) +
+              ', '.join('%s %d' % (n, x) for n, x in zip(names, v)) + ' | total %d' % v.sum())
