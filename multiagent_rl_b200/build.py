@@ -80,5 +80,36 @@ def build(force=False, verbose=True):
     return LIB
 
 
+def build_variant(name, defines):
+    """A/B or instrumented build next to the product library (tools/; load it with MPE_B200_LIB=...):
+    tmp_ab/libmpe_b200_<name>.so compiled with the given -D defines."""
+    out_dir = os.path.join(os.path.dirname(HERE), 'tmp_ab')
+    obj_dir = os.path.join(out_dir, name)
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def one(unit):
+        src, extra = unit
+        obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
+        cmd = [NVCC] + ARCH + COMMON + extra + ['-D' + d for d in defines] + ['-c', os.path.join(CSRC, src), '-o', obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed for %s:\n%s' % (src, r.stderr[-4000:]))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        objs = list(ex.map(one, UNITS))
+    lib = os.path.join(out_dir, 'libmpe_b200_%s.so' % name)
+    r = subprocess.run([NVCC] + ARCH + ['-shared', '-o', lib] + objs + ['-lcudart_static', '-ldl', '-lrt', '-lpthread'],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n%s' % r.stderr[-4000:])
+    print('built', lib)
+    return lib
+
+
 if __name__ == '__main__':
-    build(force='--force' in sys.argv)
+    if '--variant' in sys.argv:  # python -m multiagent_rl_b200.build --variant phases MPE_TC_PHASES
+        i = sys.argv.index('--variant')
+        build_variant(sys.argv[i + 1], sys.argv[i + 2:])
+    else:
+        build(force='--force' in sys.argv)
