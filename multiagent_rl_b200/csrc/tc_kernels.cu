@@ -1010,6 +1010,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
 #endif
         bar_sync_n(1, 256);  // the exchange buffers are complete
+        TL(half, 14);
 
         // ---- own tile: Gumbel-max sampling ----
         int au[N], ac[N];
@@ -1017,6 +1018,59 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const uint64_t step = FUSED ? ro.step0 + (uint64_t)it : io.step;
           const uint64_t seed = FUSED ? s.seed : io.seed;
           const int64_t gid0 = FUSED ? s.gid0 : io.gid0;
+          // Gumbel noise of all N agents of this row up front: the N * APAD/4 Philox blocks advance together and
+          // the log chains of the values run in lock-step (see bits_to_gumbel_batch)
+          float gn[N][APAD];
+#pragma unroll
+          for (int t = 0; t < N; ++t)
+#pragma unroll
+            for (int a = 0; a < APAD; ++a) gn[t][a] = 0.0f;
+          if (!FUSED && io.gumbel != nullptr) {
+            if (mine) {
+#pragma unroll
+              for (int t = 0; t < N; ++t)
+#pragma unroll
+                for (int a = 0; a < APAD; ++a)
+                  if (a < w.A) gn[t][a] = io.gumbel[(b * N + t) * w.A + a];
+            }
+          } else {
+            constexpr int NQ = APAD / 4;
+            uint4 c[N * NQ];
+#pragma unroll
+            for (int t = 0; t < N; ++t)
+#pragma unroll
+              for (int jj = 0; jj < NQ; ++jj)
+                c[t * NQ + jj] = philox_counter((uint64_t)(gid0 + b), (uint32_t)step, kDomainGumbel, t * 8 + jj);
+            philox4x32_10_batch<N * NQ>(c, philox_key(seed));
+            if (w.A == 5) {  // the movement head of every supported scenario: exactly the 5 used values per agent
+              uint32_t r[N * 5];
+              float g[N * 5];
+#pragma unroll
+              for (int t = 0; t < N; ++t) {
+                r[t * 5 + 0] = c[t * NQ].x; r[t * 5 + 1] = c[t * NQ].y; r[t * 5 + 2] = c[t * NQ].z;
+                r[t * 5 + 3] = c[t * NQ].w; r[t * 5 + 4] = c[t * NQ + 1].x;
+              }
+              bits_to_gumbel_batch<N * 5>(r, g);
+#pragma unroll
+              for (int t = 0; t < N; ++t)
+#pragma unroll
+                for (int a = 0; a < 5; ++a) gn[t][a] = g[t * 5 + a];
+            } else {
+#pragma unroll
+              for (int t = 0; t < N; ++t) {
+                uint32_t r[APAD];
+                float g[APAD];
+#pragma unroll
+                for (int jj = 0; jj < NQ; ++jj) {
+                  r[4 * jj] = c[t * NQ + jj].x; r[4 * jj + 1] = c[t * NQ + jj].y;
+                  r[4 * jj + 2] = c[t * NQ + jj].z; r[4 * jj + 3] = c[t * NQ + jj].w;
+                }
+                bits_to_gumbel_batch<APAD>(r, g);
+#pragma unroll
+                for (int a = 0; a < APAD; ++a) gn[t][a] = a < w.A ? g[a] : 0.0f;
+              }
+            }
+          }
 #pragma unroll
           for (int t = 0; t < N; ++t) {
             float z[APAD];
@@ -1025,23 +1079,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int a = 0; a < APAD / 2; ++a)
               upk(add2(lgp[t][a], own_xchg2[((size_t)t * (APAD / 2) + a) * kRows + row]), lgt[2 * a], lgt[2 * a + 1]);
             const int64_t orow = b * N + t;
-            if (!FUSED && io.gumbel != nullptr) {
 #pragma unroll
-              for (int a = 0; a < APAD; ++a) z[a] = (a < w.A && mine) ? lgt[a] + io.gumbel[orow * w.A + a] : lgt[a];
-            } else {
-#pragma unroll
-              for (int jj = 0; jj < APAD / 4; ++jj) {
-                if (4 * jj >= w.A) {
-                  z[4 * jj] = z[4 * jj + 1] = z[4 * jj + 2] = z[4 * jj + 3] = 0.0f;
-                  continue;
-                }
-                const uint4 rr = philox_raw(seed, (uint64_t)(gid0 + b), (uint32_t)step, kDomainGumbel, t * 8 + jj);
-                const uint32_t bits[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  z[4 * jj + q] = (4 * jj + q < w.A) ? lgt[4 * jj + q] + bits_to_gumbel(bits[q]) : 0.0f;
-              }
-            }
+            for (int a = 0; a < APAD; ++a) z[a] = a < w.A ? lgt[a] + gn[t][a] : 0.0f;
             int bu = 0, bc = 0;
             float best = z[0];
 #pragma unroll
@@ -1054,6 +1093,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (a >= w.A0 && a < w.A && z[a] > bcv) { bcv = z[a]; bc = a - w.A0; }
             }
             au[t] = bu; ac[t] = bc;
+            TL(half, 15 + t);
             own_act[(row * N + t) * 2] = (uint8_t)bu;
             own_act[(row * N + t) * 2 + 1] = (uint8_t)bc;
             if (!FUSED && mine && io.logits != nullptr) {
