@@ -109,6 +109,7 @@ struct Underflow<double> {
 
 // Fold finished episodes of a warp into stats = {sum ret, sum ret^2, episodes, steps}.
 __device__ __forceinline__ void fold_stats(double *stats, double ret, double n_ep, double n_steps) {
+  if (!__any_sync(0xffffffffu, n_ep != 0.0)) return;  // no episode of this warp ended in this step (the usual case)
   double a = ret * n_ep, b = ret * ret * n_ep, c = n_ep, d = n_steps;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -144,10 +144,14 @@ __device__ __forceinline__ void mma3_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t
 // Optional phase timeline (MPE_TC_TIMELINE=1): clock64 stamps of the first tile of every warpgroup, read back
 // with the (undeclared, debug-only) export mpe_debug_tc_timeline.
 __device__ unsigned long long g_tc_timeline[148 * 128];
+#ifdef MPE_TC_PHASES  // instrumented build only (python -m multiagent_rl_b200.build --variant phases MPE_TC_PHASES)
 #define TL(role, i)                                                                                              \
   do {                                                                                                           \
     if (dbg && first_tile && blockIdx.x < 148) g_tc_timeline[blockIdx.x * 128 + (role) * 32 + (i)] = clock64(); \
   } while (0)
+#else
+#define TL(role, i)
+#endif
 
 // barriers of one warpgroup's pipeline (indices into its own block of the barrier array)
 enum { B_X = 0, B_D1, B_H1, B_G, B_H, B_PER_WG };
@@ -352,9 +356,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (k > 0) { mbar_wait(&bb[B_H], ph_h); ph_h ^= 1; }  // previous cell done: G free, recurrent h in smem
             tc_fence_after();
             TL(2 + g, 1 + 2 * k);
-            mma3_ts(tmem, tmem + col_h1, tmem + col_h1 + 32, sm_w + w.off_wih[d][0], sm_w + w.off_wih[d][1], kGateN * 16, 4,
+            mma3_ts(tmem, tmem + col_h1, tmem + col_h1 + 32, sm_w + (d ? w.off_wih[1][0] : w.off_wih[0][0]), sm_w + (d ? w.off_wih[1][1] : w.off_wih[0][1]), kGateN * 16, 4,
                     id_g, false);
-            if (st > 0) mma3_ss(tmem, sm_h, sm_h + 8192, kChunkA, sm_w + w.off_whh[d][0], sm_w + w.off_whh[d][1], kGateN * 16, 2, id_g, true);
+            if (st > 0) mma3_ss(tmem, sm_h, sm_h + 8192, kChunkA, sm_w + (d ? w.off_whh[1][0] : w.off_whh[0][0]),
+                                sm_w + (d ? w.off_whh[1][1] : w.off_whh[0][1]), kGateN * 16, 2, id_g, true);
             mma_commit(&bb[B_G]);
             if (k + 1 < 2 * N) {  // dense1 of the next cell's agent runs behind the gates on the tensor pipe
               const int d2 = (k + 1) / N, s2 = k + 1 - d2 * N;
@@ -739,14 +744,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     k_tc2(EnvState<float> s, TcDev w, ActorIO io, RolloutIO ro, int max_episode_len, int64_t ntiles, int dbg) {
   static_assert(N <= 3, "k_tc2 keeps all obs operands resident");
   extern __shared__ __align__(128) unsigned char smem[];
-  const int skew = dbg >> 8;  // experiment: warpgroup 1 enters the cell pipeline this many cycles late
-  dbg &= 1;
+#ifdef MPE_TC_PHASES
   if (dbg && threadIdx.x == 0 && blockIdx.x < 148) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     g_tc_timeline[blockIdx.x * 128 + 64] = gt;
     g_tc_timeline[blockIdx.x * 128 + 66] = clock64();
   }
+#endif
   using Dm = Dims<SC, N>;
   const int D = FUSED ? Dm::D : w.D;
   const int R = N * D;
@@ -807,9 +812,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_wait(&bb[B_H1], ph_h1); ph_h1 ^= 1;
             if (k > 0) { mbar_wait(&bb[B_H], ph_h); ph_h ^= 1; }
             tc_fence_after();
-            mma3_ts(tmem, tmem + col_h1, tmem + col_h1 + 32, sm_w + w.off_wih[d][0], sm_w + w.off_wih[d][1], kGateN * 16, 4,
+            mma3_ts(tmem, tmem + col_h1, tmem + col_h1 + 32, sm_w + (d ? w.off_wih[1][0] : w.off_wih[0][0]), sm_w + (d ? w.off_wih[1][1] : w.off_wih[0][1]), kGateN * 16, 4,
                     id_g, false);
-            if (st > 0) mma3_ss(tmem, sm_h, sm_h + 8192, kChunkA, sm_w + w.off_whh[d][0], sm_w + w.off_whh[d][1], kGateN * 16, 2, id_g, true);
+            if (st > 0) mma3_ss(tmem, sm_h, sm_h + 8192, kChunkA, sm_w + (d ? w.off_whh[1][0] : w.off_whh[0][0]),
+                                sm_w + (d ? w.off_whh[1][1] : w.off_whh[0][1]), kGateN * 16, 2, id_g, true);
             mma_commit(&bb[B_G]);
             if (k + 1 < 2 * N) {
               const int d2 = (k + 1) / N, s2 = k + 1 - d2 * N;
@@ -834,9 +840,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     float *stage_obs = reinterpret_cast<float *>(own_x), *stage_rew = stage_obs + kRows * R;
     uint32_t ph_d1[2] = {0, 0}, ph_g[2] = {0, 0};
     mbar_wait(&bars[0], 0);
+#ifdef MPE_TC_PHASES
     if (dbg && tid == 0 && blockIdx.x < 148) g_tc_timeline[blockIdx.x * 128 + 67] = clock64();
+#endif
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+#ifdef MPE_TC_PHASES
       if (dbg && tid == 0 && blockIdx.x < 148 && pair != blockIdx.x) g_tc_timeline[blockIdx.x * 128 + 68] = clock64();
+#endif
       const int64_t tile = pair * 2 + own;                 // the tile this warpgroup owns (may not exist)
       const int64_t env0 = tile * kRows;
       const int64_t nb = FUSED ? s.B : io.B;
@@ -984,10 +994,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           }
         };
-        if (skew > 0 && half == 1) {
-          const long long t0 = clock64();
-          while (clock64() - t0 < skew) {}
-        }
         // ---- the interleaved cell pipeline:  E1(A,0) | E1(B,k) C(A,k) E1(A,k+1) C(B,k) | ...  (tile A = 0, B = 1) ----
         using I0 = std::integral_constant<int, 0>;
         using I1 = std::integral_constant<int, 1>;
@@ -1010,6 +1016,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
 #endif
         bar_sync_n(1, 256);  // the exchange buffers are complete
+        TL(half, 14);
         TL(half, 14);
 
         // ---- own tile: Gumbel-max sampling ----
@@ -1114,7 +1121,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           double ret = 0.0, n_ep = 0.0, n_steps = 0.0;
           if (mine) {
             e.load(s, b);
+            TL(half, 18);
             e.physics(au, s);
+            TL(half, 19);
             if (SC == kReference) {
 #pragma unroll
               for (int i = 0; i < 2; ++i)
@@ -1140,12 +1149,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               s.ep_ret[b] = ep_ret; s.tstep[b] = ts;
             }
           }
+          TL(half, 21);
           fold_stats(s.stats, ret, n_ep, n_steps);
           float *g_obs = (ro.obs_next != nullptr && valid > 0) ? ro.obs_next + (toff + env0) * R : nullptr;
           float *g_rew = (ro.rew != nullptr && valid > 0) ? ro.rew + (toff + env0) * N : nullptr;
           const bool tma_ok = valid == kRows && ((reinterpret_cast<uintptr_t>(g_obs) | reinterpret_cast<uintptr_t>(g_rew)) & 15) == 0;
           if (tma_ok) fence_proxy_async_smem();
           bar_sync_n(2 + own, 128);
+          TL(half, 22);
           if (g_obs != nullptr || g_rew != nullptr) {
             if (tma_ok) {
               if (row == 0) {
@@ -1185,6 +1196,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int k = 0; k < 10; ++k) s.comm[((int64_t)i * 10 + k) * s.B + b] = comm[i][k];
             }
           }
+          TL(half, 23);
           if (row == 0 && tma_ok && (g_obs != nullptr || g_rew != nullptr)) bulk_wait_read_all();
         } else {
           bar_sync_n(2 + own, 128);
@@ -1209,12 +1221,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_free(tmem_base, 512);
+#ifdef MPE_TC_PHASES
   if (dbg && threadIdx.x == 0 && blockIdx.x < 148) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     g_tc_timeline[blockIdx.x * 128 + 65] = gt;
     g_tc_timeline[blockIdx.x * 128 + 69] = clock64();
   }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1238,8 +1252,7 @@ static cudaError_t launch_tc2_t(const EnvState<float> &s, const TcDev &w, const 
   const int64_t pairs = (ntiles + 1) / 2;
   const int grid = (int)(pairs < nsm ? pairs : nsm);
   k_tc2<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles,
-                                                           (getenv("MPE_TC_TIMELINE") != nullptr ? 1 : 0) |
-                                                               (getenv("MPE_TC_SKEW") ? atoi(getenv("MPE_TC_SKEW")) << 8 : 0));
+                                                           getenv("MPE_TC_TIMELINE") != nullptr ? 1 : 0);
   return cudaGetLastError();
 }
 
