@@ -174,7 +174,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float exp_neg(float x) { return ex2_approx(fminf(-1.4426950408889634f * x, 57.0f)); }
 
 // dense1 epilogue for 32 hidden units of one env row: h1 = relu(D1/16 + b1) -> fp16 hi/lo, 16 packed columns each
-__device__ __forceinline__ void dense1_half(const uint32_t (&v)[32], const float *b1, uint32_t taddr_hi) {
+__device__ __forceinline__ void dense1_half(const uint32_t (&v)[32], const float *b1, uint32_t taddr_hi,
+                                            uint32_t lo_off = 32) {
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -188,7 +189,7 @@ __device__ __forceinline__ void dense1_half(const uint32_t (&v)[32], const float
     lo[j] = pack_h2(l0, l1);
   }
   tmem_st16(taddr_hi, hi);
-  tmem_st16(taddr_hi + 32, lo);
+  tmem_st16(taddr_hi + lo_off, lo);
 }
 
 // ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot for two lanes of cell math ----
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const uint32_t id_g = make_idesc_f16(128, 128), id_d1 = make_idesc_f16(128, 64);
       mbar_wait(&bars[0], 0);
       for (int64_t tile = tile0; tile < ntiles; tile += tile_stride) {
-        const bool first_tile = tile == tile0;
+        [[maybe_unused]] const bool first_tile = tile == tile0;
         for (int it = 0; it < T; ++it) {
           mbar_wait(&bb[B_X], ph_x); ph_x ^= 1;
           tc_fence_after();
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const int valid = (int)((nb - env0) < kRows ? (nb - env0) : kRows);
       const bool mine = row < valid;
       const int64_t b = env0 + row;
-      const bool first_tile = tile == tile0 && row == 0;
+      [[maybe_unused]] const bool first_tile = tile == tile0 && row == 0;
       for (int it = 0; it < T; ++it) {
         TL(g, 0);
         // ---- observations -> fp16 hi/lo A operands ----
@@ -784,7 +785,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int T = FUSED ? ro.T : 1;
-  const uint32_t col_d1 = 128, col_h1 = 192;
+  // TMEM columns of a tile: gate accumulators [0,128) and two 64-column h1 slots at 128 / 192.  A slot first
+  // receives the dense1 accumulators of an agent and is then converted IN PLACE into that agent's h1 operand
+  // (thread half h owns columns [32h, 32h+32) of the slot: fp16 hi pairs in the first 16, lo pairs in the last 16).
+  // Agent t lives in slot t & 1, so the backward pass finds the h1 of agents N-1 and N-2 still resident and only
+  // agents that were overwritten (t + 2 < N) are recomputed: 4 dense1 GEMMs + epilogues per tile instead of 6.
+  auto agent_of = [](int k) { return k < N ? k : 2 * N - 1 - k; };
+  auto need_e1 = [&](int k) { return k < N || agent_of(k) + 2 < N; };
+  auto slot_col = [](int t) { return 128u + 64u * (uint32_t)(t & 1); };
   const int64_t npairs = (ntiles + 1) / 2;
 
   if (warp >= 8) {
@@ -803,24 +811,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           tc_fence_after();
           auto dense1 = [&](int t) {
             const unsigned char *xh = sm_x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
-            mma3_ss(tmem + col_d1, xh, xl, kChunkA, sm_w + w.off_w1[0], sm_w + w.off_w1[1], kHid * 16, Kx / 16, id_d1, false);
+            mma3_ss(tmem + slot_col(t), xh, xl, kChunkA, sm_w + w.off_w1[0], sm_w + w.off_w1[1], kHid * 16, Kx / 16, id_d1, false);
             mma_commit(&bb[B_D1]);
           };
           dense1(0);
           for (int k = 0; k < 2 * N; ++k) {
-            const int d = k / N, st = k - d * N;
-            mbar_wait(&bb[B_H1], ph_h1); ph_h1 ^= 1;
+            const int d = k >= N ? 1 : 0, st = k - d * N;
+            if (need_e1(k)) { mbar_wait(&bb[B_H1], ph_h1); ph_h1 ^= 1; }
             if (k > 0) { mbar_wait(&bb[B_H], ph_h); ph_h ^= 1; }
             tc_fence_after();
-            mma3_ts(tmem, tmem + col_h1, tmem + col_h1 + 32, sm_w + (d ? w.off_wih[1][0] : w.off_wih[0][0]), sm_w + (d ? w.off_wih[1][1] : w.off_wih[0][1]), kGateN * 16, 4,
-                    id_g, false);
+            const uint32_t a0 = tmem + slot_col(agent_of(k));  // K blocks 0,1 from half 0 of the slot, 2,3 from half 1
+            const unsigned char *wih_hi = sm_w + (d ? w.off_wih[1][0] : w.off_wih[0][0]);
+            const unsigned char *wih_lo = sm_w + (d ? w.off_wih[1][1] : w.off_wih[0][1]);
+            mma3_ts(tmem, a0, a0 + 16, wih_hi, wih_lo, kGateN * 16, 2, id_g, false);
+            mma3_ts(tmem, a0 + 32, a0 + 48, wih_hi + 4 * kGateN * 16, wih_lo + 4 * kGateN * 16, kGateN * 16, 2, id_g, true);
             if (st > 0) mma3_ss(tmem, sm_h, sm_h + 8192, kChunkA, sm_w + (d ? w.off_whh[1][0] : w.off_whh[0][0]),
                                 sm_w + (d ? w.off_whh[1][1] : w.off_whh[0][1]), kGateN * 16, 2, id_g, true);
             mma_commit(&bb[B_G]);
-            if (k + 1 < 2 * N) {
-              const int d2 = (k + 1) / N, s2 = k + 1 - d2 * N;
-              dense1(d2 == 0 ? s2 : N - 1 - s2);
-            }
+            // the next cell's dense1 goes behind this gate GEMM; its slot held agent (next - 2), whose last reader
+            // was issued before this point (the tensor pipe executes in order)
+            if (k + 1 < 2 * N && need_e1(k + 1)) dense1(agent_of(k + 1));
           }
           mbar_wait(&bb[B_H], ph_h); ph_h ^= 1;
         }
@@ -853,7 +863,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const int valid = tile < ntiles ? (int)((nb - env0) < kRows ? (nb - env0) : kRows) : 0;
       const bool mine = row < valid;
       const int64_t b = env0 + row;
-      const bool first_tile = pair == blockIdx.x && row == 0;
+      [[maybe_unused]] const bool first_tile = pair == blockIdx.x && row == 0;
       for (int it = 0; it < T; ++it) {
         TL(half, 0);
         // ---- own tile: observations -> fp16 hi/lo A operands ----
@@ -919,19 +929,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #define TS(i)
 #endif
         // E1(X): dense1 epilogue of this thread's 32 hidden columns of tile X's next cell
-        auto E1 = [&](auto XT) {
+        auto E1 = [&](auto XT, int k) {
           constexpr int X = decltype(XT)::value;
           uint64_t *bb = bars + 1 + X * B_PER_WG;
-          const uint32_t tmem = tmem_base + X * 256;
+          const uint32_t tmem = tmem_base + X * 256 + slot_col(agent_of(k)) + half * 32;
           TS(9);
           mbar_wait(&bb[B_D1], ph_d1[X]); ph_d1[X] ^= 1;
           tc_fence_after();
           TS(0);
           uint32_t v0[32];
-          tmem_ld32(tmem + lane_base + col_d1 + half * 32, v0);
+          tmem_ld32(tmem + lane_base, v0);
           tmem_wait_ld();
           TS(1);
-          dense1_half(v0, b1 + half * 32, tmem + lane_base + col_h1 + half * 16);
+          dense1_half(v0, b1 + half * 32, tmem + lane_base, 16);  // in place: hi pairs, then lo pairs
           TS(2);
           tmem_wait_st();
           tc_fence_before();
@@ -998,14 +1008,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         using I0 = std::integral_constant<int, 0>;
         using I1 = std::integral_constant<int, 1>;
         TL(half, 1);
-        E1(I0{});
+        E1(I0{}, 0);
 #pragma unroll 1
         for (int k = 0; k < 2 * N; ++k) {
           TL(half, 2 + 2 * k);
-          E1(I1{});
+          if (need_e1(k)) E1(I1{}, k);
           CC(I0{}, k, cA);
           TL(half, 3 + 2 * k);
-          if (k + 1 < 2 * N) E1(I0{});
+          if (k + 1 < 2 * N && need_e1(k + 1)) E1(I0{}, k + 1);
           CC(I1{}, k, cB);
         }
         TL(half, 28);
