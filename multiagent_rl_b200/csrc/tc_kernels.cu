@@ -734,16 +734,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // dense2 sums of the units it does not own reach it through a shared-memory exchange buffer.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t tc2_tile_bytes(int N, int Kx, int APAD) {
-  return tc_x_bytes(N, Kx) + 16384 + (size_t)((kRows * N * 2 + 127) / 128 * 128) + (size_t)N * APAD * kRows * 4;
+  // obs operands, recurrent h operand, action bytes, and (teams of <= 3) the dense2 exchange buffer; larger teams
+  // keep every cell's dense2 share in the global scratch instead
+  return tc_x_bytes(N, Kx) + 16384 + (size_t)((kRows * N * 2 + 127) / 128 * 128) + (N <= 3 ? (size_t)N * APAD * kRows * 4 : 0);
 }
+enum { B2_XR = 0, B2_XF = 2, B2_EXTRA = 4 };  // per tile: obs operand buffer 0/1 ready, buffer 0/1 free again
 __host__ __device__ inline size_t tc2_smem_bytes(uint32_t wbytes, int N, int Kx, int APAD) {
-  return (size_t)wbytes + 2 * tc2_tile_bytes(N, Kx, APAD) + (1 + 2 * B_PER_WG) * 8 + 64;
+  return (size_t)wbytes + 2 * tc2_tile_bytes(N, Kx, APAD) + (1 + 2 * B_PER_WG + 2 * B2_EXTRA) * 8 + 64;
 }
+// dense2 shares of large teams: [CTA][tile 0/1][warpgroup half][cell 0..2N-1][APAD/2 packed pairs][128 rows] f2
+__host__ __device__ inline size_t tc2_scratch_f2_per_cta(int N, int APAD) { return (size_t)2 * 2 * 2 * N * (APAD / 2) * kRows; }
+__host__ __device__ constexpr int tc2_threads(int N) { return N > 3 ? 384 : 320; }  // + two service warps for large teams
 
 template <int SC, int N, bool FUSED, int APAD>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(tc2_threads(N), 1)
     k_tc2(EnvState<float> s, TcDev w, ActorIO io, RolloutIO ro, int max_episode_len, int64_t ntiles, int dbg) {
-  static_assert(N <= 3, "k_tc2 keeps all obs operands resident");
+  // Large teams (N > 3, actor only): the obs operands do not fit next to the weights, so a per-tile OPERAND WARP
+  // (warps 10 / 11; the register file is allocated for 12 warps anyway) streams them from the caller's tensor into a
+  // two-deep operand ring one or two cells ahead of the dense1 GEMMs, and every cell's dense2 share goes to its own
+  // global scratch row (L2 resident) from which the owner warpgroup completes the logits and samples after the
+  // pipeline.  Inside the pipeline the eight epilogue warps do nothing but the dense1 epilogue and the cell math.
+  // (Measured alternatives: refilling from the epilogue warps - 400 B of spills and exposed load latency, slower than
+  // k_tc; a service warp that also samples one cell behind the pipeline - its ~11 k instructions per tile slow the
+  // two sub-partitions it shares and with them the whole barrier-coupled pipeline.)
+  constexpr bool kJit = N > 3;
+  static_assert(!(kJit && FUSED), "the fused World.step keeps every agent of a row in registers: teams of <= 3");
   extern __shared__ __align__(128) unsigned char smem[];
 #ifdef MPE_TC_PHASES
   if (dbg && threadIdx.x == 0 && blockIdx.x < 148) {
@@ -762,7 +777,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const size_t tile_bytes = tc2_tile_bytes(N, Kx, APAD);
   unsigned char *sm_w = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + w.bytes + 2 * tile_bytes);  // [0] = weights, then 2 x B_PER_WG
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 1 + 2 * B_PER_WG);
+  uint64_t *xbars = bars + 1 + 2 * B_PER_WG;  // [tile][B2_XR + buf | B2_XF + buf]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xbars + 2 * B2_EXTRA);
   auto tile_smem = [&](int X) { return smem + w.bytes + X * tile_bytes; };
 
   if (tid == 0) {
@@ -774,6 +790,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       mbar_init(&bb[B_H1], 256);  // both warpgroups converted their half of h1
       mbar_init(&bb[B_G], 1);
       mbar_init(&bb[B_H], 256);   // both warpgroups finished their half of the cell
+      for (int q = 0; q < 2; ++q) {
+        mbar_init(&xbars[g * B2_EXTRA + B2_XR + q], 32);  // the service warp filled operand buffer q
+        mbar_init(&xbars[g * B2_EXTRA + B2_XF + q], 1);   // the dense1 GEMM reading buffer q has completed
+      }
     }
     mbar_fence_init();
     mbar_expect_tx(&bars[0], w.bytes);
@@ -794,27 +814,102 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   auto need_e1 = [&](int k) { return k < N || agent_of(k) + 2 < N; };
   auto slot_col = [](int t) { return 128u + 64u * (uint32_t)(t & 1); };
   const int64_t npairs = (ntiles + 1) / 2;
+  // large teams: index of cell j in the sequence of cells that have a dense1 GEMM (the two resident backward cells
+  // N, N+1 are skipped); the operand ring buffer of that GEMM is (index & 1)
+  auto d1_index = [](int j) { return j < N ? j : j - 2; };
 
-  if (warp >= 8) {
+  if (kJit && warp >= 10) {
+    // =============================== operand warp of tile X = warp - 10 (large teams) ===============================
+    // obs[b][t][:] of the caller's tensor -> fp16 hi/lo ring buffers, in GEMM order, one or two cells ahead of the
+    // dense1 GEMMs.  Lane l serves rows l, l+32, l+64, l+96; ring buffer q is reused once the dense1 GEMM that read
+    // it has completed (B2_XF, tcgen05.commit).
+    const int X = warp - 10, lane = tid & 31;
+    unsigned char *sm_x = tile_smem(X);
+    uint64_t *xb2 = xbars + X * B2_EXTRA;
+    uint32_t ph_xf = 0, filled = 0;  // bit q: phase parity of / first fill done for ring buffer q
+    const bool vec2 = (reinterpret_cast<uintptr_t>(io.obs) & 7) == 0 && (D & 1) == 0;
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int64_t tile = pair * 2 + X, env0 = tile * kRows;
+      const int valid = tile < ntiles ? (int)((io.B - env0) < kRows ? (io.B - env0) : kRows) : 0;
+#pragma unroll 1
+      for (int j = 0; j < 2 * N; ++j) {
+        if (!need_e1(j)) continue;
+        const int t = agent_of(j), q = d1_index(j) & 1;
+        if ((filled >> q) & 1u) { mbar_wait(&xb2[B2_XF + q], (ph_xf >> q) & 1u); ph_xf ^= 1u << q; }
+        filled |= 1u << q;
+        unsigned char *xh = sm_x + (size_t)(q * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
+#pragma unroll 1
+        for (int rp = 0; rp < 2; ++rp) {  // two rows per round: 2 x 32 values in registers, loads of both in flight
+          float xr[2][32];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int r = lane + 32 * (2 * rp + u);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) xr[u][k] = 0.0f;
+            if (r < valid) {
+              const float *src = io.obs + (env0 + r) * R + t * D;
+              if (vec2) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  if (2 * k < D) {
+                    const float2 v = *reinterpret_cast<const float2 *>(src + 2 * k);
+                    xr[u][2 * k] = v.x; xr[u][2 * k + 1] = v.y;
+                  }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                  if (k < D) xr[u][k] = src[k];
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int r = lane + 32 * (2 * rp + u);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c * 8 < Kx) {
+                const float v[8] = {xr[u][c * 8], xr[u][c * 8 + 1], xr[u][c * 8 + 2], xr[u][c * 8 + 3],
+                                    xr[u][c * 8 + 4], xr[u][c * 8 + 5], xr[u][c * 8 + 6], xr[u][c * 8 + 7]};
+                store_chunk_split(xh + c * kChunkA, xl + c * kChunkA, r, v);
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&xb2[B2_XR + q]);
+      }
+    }
+  } else if (warp >= 8) {
     // =============================== MMA issuer of tile X = warp - 8 ===============================
     const int X = warp - 8;
     if ((tid & 31) == 0) {
       unsigned char *sm_x = tile_smem(X), *sm_h = sm_x + xb;
       uint64_t *bb = bars + 1 + X * B_PER_WG;
       const uint32_t tmem = tmem_base + X * 256;
-      uint32_t ph_x = 0, ph_h1 = 0, ph_h = 0;
+      uint32_t ph_x = 0, ph_h1 = 0, ph_h = 0, ph_xr = 0;  // ph_xr: bit q = phase parity of ring buffer q
+      uint64_t *xb2 = xbars + X * B2_EXTRA;
       const uint32_t id_g = make_idesc_f16(128, 128), id_d1 = make_idesc_f16(128, 64);
       mbar_wait(&bars[0], 0);
       for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
         for (int it = 0; it < T; ++it) {
-          mbar_wait(&bb[B_X], ph_x); ph_x ^= 1;
-          tc_fence_after();
-          auto dense1 = [&](int t) {
-            const unsigned char *xh = sm_x + (size_t)(t * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
+          if constexpr (!kJit) {
+            mbar_wait(&bb[B_X], ph_x); ph_x ^= 1;
+            tc_fence_after();
+          }
+          // dense1 GEMM of cell j -> the agent's h1 slot.  Small teams: operand buffer = agent (all resident).
+          // Large teams: ring buffer (dense1 index & 1), filled by the service warp; its completion frees the buffer.
+          auto dense1_cell = [&](int j) {
+            const int t = agent_of(j), q = d1_index(j) & 1, xs = kJit ? q : t;
+            if constexpr (kJit) {
+              mbar_wait(&xb2[B2_XR + q], (ph_xr >> q) & 1u); ph_xr ^= 1u << q;
+              tc_fence_after();
+            }
+            const unsigned char *xh = sm_x + (size_t)(xs * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
             mma3_ss(tmem + slot_col(t), xh, xl, kChunkA, sm_w + w.off_w1[0], sm_w + w.off_w1[1], kHid * 16, Kx / 16, id_d1, false);
             mma_commit(&bb[B_D1]);
+            if constexpr (kJit) mma_commit(&xb2[B2_XF + q]);
           };
-          dense1(0);
+          dense1_cell(0);
           for (int k = 0; k < 2 * N; ++k) {
             const int d = k >= N ? 1 : 0, st = k - d * N;
             if (need_e1(k)) { mbar_wait(&bb[B_H1], ph_h1); ph_h1 ^= 1; }
@@ -830,7 +925,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mma_commit(&bb[B_G]);
             // the next cell's dense1 goes behind this gate GEMM; its slot held agent (next - 2), whose last reader
             // was issued before this point (the tensor pipe executes in order)
-            if (k + 1 < 2 * N && need_e1(k + 1)) dense1(agent_of(k + 1));
+            if (k + 1 < 2 * N && need_e1(k + 1)) dense1_cell(k + 1);
           }
           mbar_wait(&bb[B_H], ph_h); ph_h ^= 1;
         }
@@ -849,6 +944,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const f2 *own_xchg2 = reinterpret_cast<const f2 *>(own_act + (kRows * N * 2 + 127) / 128 * 128);
     float *stage_obs = reinterpret_cast<float *>(own_x), *stage_rew = stage_obs + kRows * R;
     uint32_t ph_d1[2] = {0, 0}, ph_g[2] = {0, 0};
+    // large teams: this CTA's dense2-share scratch, [tile][half][cell][pair of head entries][row]
+    f2 *scr = kJit ? reinterpret_cast<f2 *>(w.scratch) + (size_t)blockIdx.x * tc2_scratch_f2_per_cta(N, APAD) : nullptr;
     mbar_wait(&bars[0], 0);
 #ifdef MPE_TC_PHASES
     if (dbg && tid == 0 && blockIdx.x < 148) g_tc_timeline[blockIdx.x * 128 + 67] = clock64();
@@ -866,8 +963,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       [[maybe_unused]] const bool first_tile = pair == blockIdx.x && row == 0;
       for (int it = 0; it < T; ++it) {
         TL(half, 0);
-        // ---- own tile: observations -> fp16 hi/lo A operands ----
-        {
+        // ---- own tile: observations -> fp16 hi/lo A operands (large teams: the service warp streams them) ----
+        if constexpr (!kJit) {
           Env<float, SC, N> e;
           float comm[2][10];
           if (FUSED && mine) {
@@ -903,13 +1000,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&bars[1 + own * B_PER_WG + B_X]);
+        if constexpr (!kJit) {
+          fence_proxy_async_smem();
+          mbar_arrive(&bars[1 + own * B_PER_WG + B_X]);
+        }
 
         // dense2 sums of the OWN tile's rows over this thread's 16 units (+ bias), packed pairs of head entries
-        f2 lgp[N][APAD / 2];
+        constexpr int NLG = kJit ? 1 : N;
+        f2 lgp[NLG][APAD / 2];
 #pragma unroll
-        for (int t = 0; t < N; ++t)
+        for (int t = 0; t < NLG; ++t)
 #pragma unroll
           for (int a = 0; a < APAD / 2; ++a) lgp[t][a] = pk(b2[2 * a], b2[2 * a + 1]);
 
@@ -952,7 +1052,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         auto CC = [&](auto XT, int k, f2 (&c)[2][4]) {
           constexpr int X = decltype(XT)::value;
           const int d = k >= N ? 1 : 0, st = k - d * N;
-          const int t = d == 0 ? st : N - 1 - st;
+          [[maybe_unused]] const int t = d == 0 ? st : N - 1 - st;
           uint64_t *bb = bars + 1 + X * B_PER_WG;
           const uint32_t tmem = tmem_base + X * 256;
           unsigned char *sm_h = tile_smem(X) + xb;
@@ -985,9 +1085,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           tc_fence_before();
           mbar_arrive(&bb[B_H]);
           TS(8);
-          if (X == own) {
+          if constexpr (kJit) {
+            // every cell's share goes to its own scratch row (no read-modify-write); the owner warpgroup completes
+            // the logits from the four shares of an agent after the pipeline
+            f2 *dst = scr + ((size_t)((X * 2 + half) * 2 * N + k) * (APAD / 2)) * kRows + row;
 #pragma unroll
-            for (int tt = 0; tt < N; ++tt)
+            for (int a = 0; a < APAD / 2; ++a) dst[a * kRows] = pl[a];
+          } else if (X == own) {
+#pragma unroll
+            for (int tt = 0; tt < NLG; ++tt)
               if (tt == t) {
 #pragma unroll
                 for (int a = 0; a < APAD / 2; ++a) lgp[tt][a] = add2(lgp[tt][a], pl[a]);
@@ -1025,13 +1131,104 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           for (int i = 0; i < 10; ++i) g_tc_timeline[blockIdx.x * 128 + 96 + half * 10 + i] = acc[i];
         }
 #endif
-        bar_sync_n(1, 256);  // the exchange buffers are complete
-        TL(half, 14);
+        bar_sync_n(1, 256);  // the exchange buffers / scratch shares of both warpgroups are complete
         TL(half, 14);
 
         // ---- own tile: Gumbel-max sampling ----
         int au[N], ac[N];
-        {
+        if constexpr (kJit) {
+          // groups of G agents: logits = bias + the four scratch shares (two warpgroups x two directions); the G * 2
+          // Philox blocks and the G * 5 Gumbel transforms of a group run in lock-step
+          constexpr int G = (N % 3 == 0) ? 3 : 2, NQ = APAD / 4;
+#pragma unroll 1
+          for (int t0 = 0; t0 < N; t0 += G) {
+            float lgt[G][APAD], gn[G][APAD];
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+              const int t = t0 + u, kf = t, kb = 2 * N - 1 - t;
+              auto at = [&](int hf, int k) { return scr + ((size_t)((own * 2 + hf) * 2 * N + k) * (APAD / 2)) * kRows + row; };
+#pragma unroll
+              for (int a = 0; a < APAD / 2; ++a) {
+                const f2 sf = add2(at(0, kf)[a * kRows], at(1, kf)[a * kRows]);
+                const f2 sb = add2(at(0, kb)[a * kRows], at(1, kb)[a * kRows]);
+                upk(add2(add2(lgp[0][a], sf), sb), lgt[u][2 * a], lgt[u][2 * a + 1]);
+              }
+#pragma unroll
+              for (int a = 0; a < APAD; ++a) gn[u][a] = 0.0f;
+            }
+            if (io.gumbel != nullptr) {
+              if (mine) {
+#pragma unroll
+                for (int u = 0; u < G; ++u)
+#pragma unroll
+                  for (int a = 0; a < APAD; ++a)
+                    if (a < w.A) gn[u][a] = io.gumbel[(b * N + t0 + u) * w.A + a];
+              }
+            } else {
+              uint4 c[G * NQ];
+#pragma unroll
+              for (int u = 0; u < G; ++u)
+#pragma unroll
+                for (int jj = 0; jj < NQ; ++jj)
+                  c[u * NQ + jj] = philox_counter((uint64_t)(io.gid0 + b), (uint32_t)io.step, kDomainGumbel, (t0 + u) * 8 + jj);
+              philox4x32_10_batch<G * NQ>(c, philox_key(io.seed));
+              if (w.A == 5) {
+                uint32_t r[G * 5];
+                float g[G * 5];
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                  r[u * 5 + 0] = c[u * NQ].x; r[u * 5 + 1] = c[u * NQ].y; r[u * 5 + 2] = c[u * NQ].z;
+                  r[u * 5 + 3] = c[u * NQ].w; r[u * 5 + 4] = c[u * NQ + 1].x;
+                }
+                bits_to_gumbel_batch<G * 5>(r, g);
+#pragma unroll
+                for (int u = 0; u < G; ++u)
+#pragma unroll
+                  for (int a = 0; a < 5; ++a) gn[u][a] = g[u * 5 + a];
+              } else {
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                  uint32_t r[APAD];
+                  float g[APAD];
+#pragma unroll
+                  for (int jj = 0; jj < NQ; ++jj) {
+                    r[4 * jj] = c[u * NQ + jj].x; r[4 * jj + 1] = c[u * NQ + jj].y;
+                    r[4 * jj + 2] = c[u * NQ + jj].z; r[4 * jj + 3] = c[u * NQ + jj].w;
+                  }
+                  bits_to_gumbel_batch<APAD>(r, g);
+#pragma unroll
+                  for (int a = 0; a < APAD; ++a) gn[u][a] = a < w.A ? g[a] : 0.0f;
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+              const int t = t0 + u;
+              int bu = 0, bc = 0;
+              float best = lgt[u][0] + gn[u][0];
+#pragma unroll
+              for (int a = 1; a < APAD; ++a) {
+                const float z = lgt[u][a] + gn[u][a];
+                if (a < w.A0 && z > best) { best = z; bu = a; }
+              }
+              if (w.A1 > 0) {
+                float bcv = -INFINITY;
+#pragma unroll
+                for (int a = 0; a < APAD; ++a) {
+                  const float z = lgt[u][a] + gn[u][a];
+                  if (a >= w.A0 && a < w.A && z > bcv) { bcv = z; bc = a - w.A0; }
+                }
+              }
+              own_act[(row * N + t) * 2] = (uint8_t)bu;
+              own_act[(row * N + t) * 2 + 1] = (uint8_t)bc;
+              if (mine && io.logits != nullptr) {
+#pragma unroll
+                for (int a = 0; a < APAD; ++a)
+                  if (a < w.A) io.logits[(b * N + t) * w.A + a] = lgt[u][a];
+              }
+            }
+          }
+        } else {
           const uint64_t step = FUSED ? ro.step0 + (uint64_t)it : io.step;
           const uint64_t seed = FUSED ? s.seed : io.seed;
           const int64_t gid0 = FUSED ? s.gid0 : io.gid0;
@@ -1261,7 +1458,7 @@ static cudaError_t launch_tc2_t(const EnvState<float> &s, const TcDev &w, const 
   const int nsm = sm_count_tc();
   const int64_t pairs = (ntiles + 1) / 2;
   const int grid = (int)(pairs < nsm ? pairs : nsm);
-  k_tc2<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles,
+  k_tc2<SC, N, FUSED, APAD><<<grid, tc2_threads(N), smem, st>>>(s, w, io, ro, max_episode_len, ntiles,
                                                            getenv("MPE_TC_TIMELINE") != nullptr ? 1 : 0);
   return cudaGetLastError();
 }
@@ -1269,7 +1466,7 @@ static cudaError_t launch_tc2_t(const EnvState<float> &s, const TcDev &w, const 
 template <int SC, int N, bool FUSED, int APAD>
 static cudaError_t launch_tc_t(const EnvState<float> &s, const TcDev &w, const ActorIO &io, const RolloutIO &ro,
                                int max_episode_len, int64_t nenvs, cudaStream_t st) {
-  if constexpr (N <= 3) {
+  if constexpr (N <= 3 || !FUSED) {
     static const bool v1 = getenv("MPE_TC_V1") != nullptr;  // A/B switch: the two-independent-pipelines kernel
     if (!v1 && tc2_smem_bytes(w.bytes, N, w.Kx, APAD) <= 227 * 1024)
       return launch_tc2_t<SC, N, FUSED, APAD>(s, w, io, ro, max_episode_len, nenvs, st);
@@ -1290,7 +1487,10 @@ bool tc_actor_supported(const TcDev &w, int N) {
   return tc_supported(w) && (N == 2 || N == 3 || ((N == 4 || N == 6 || N == 9 || N == 12) && w.scratch != nullptr));
 }
 bool tc_rollout_supported(const TcDev &w, int N) { return tc_supported(w) && (N == 2 || N == 3); }
-size_t tc_scratch_floats(int sm_count) { return (size_t)sm_count * 2 * 12 * 16 * kRows; }
+size_t tc_scratch_floats(int sm_count) {  // the larger of k_tc's forward shares and k_tc2's per-cell shares (N = 12, APAD = 16)
+  const size_t v1 = (size_t)sm_count * 2 * 12 * 16 * kRows, v2 = (size_t)sm_count * tc2_scratch_f2_per_cta(12, 16) * 2;
+  return v1 > v2 ? v1 : v2;
+}
 
 cudaError_t launch_actor_forward_tc(const TcDev &w, const ActorIO &io, cudaStream_t st) {
   EnvState<float> s{};

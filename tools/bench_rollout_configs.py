@@ -11,6 +11,8 @@ from oracle import actor_ref  # noqa: E402
 
 CONFIGS = [('simple_spread', None, 65536), ('simple_spread', 6, 65536), ('simple_spread', 9, 32768),
            ('simple_spread', 12, 32768), ('simple_reference', None, 65536), ('simple_speaker_listener', None, 65536)]
+# the same at 1,048,576 envs per GPU (no tail quantisation: thousands of tile pairs per SM)
+CONFIGS += [(s, n, 1 << 20) for s, n, _ in CONFIGS]
 for scen, n, B in CONFIGS:
     env = m.make_env(scen, n=n, num_envs=B, batched=True, seed=1, max_episode_len=25)
     A = [5, 10] if scen == 'simple_reference' else 5
