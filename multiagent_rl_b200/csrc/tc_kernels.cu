@@ -734,9 +734,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // dense2 sums of the units it does not own reach it through a shared-memory exchange buffer.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t tc2_tile_bytes(int N, int Kx, int APAD) {
-  // obs operands, recurrent h operand, action bytes, and (teams of <= 3) the dense2 exchange buffer; larger teams
-  // keep every cell's dense2 share in the global scratch instead
-  return tc_x_bytes(N, Kx) + 16384 + (size_t)((kRows * N * 2 + 127) / 128 * 128) + (N <= 3 ? (size_t)N * APAD * kRows * 4 : 0);
+  // obs operands, recurrent h operand, action bytes, and (teams of <= 3 with one head) the dense2 exchange buffer;
+  // larger teams and the two-head simple_reference actor keep the dense2 shares in the global scratch instead
+  return tc_x_bytes(N, Kx) + 16384 + (size_t)((kRows * N * 2 + 127) / 128 * 128) + (N <= 3 && APAD <= 8 ? (size_t)N * APAD * kRows * 4 : 0);
 }
 enum { B2_XR = 0, B2_XF = 2, B2_EXTRA = 4 };  // per tile: obs operand buffer 0/1 ready, buffer 0/1 free again
 __host__ __device__ inline size_t tc2_smem_bytes(uint32_t wbytes, int N, int Kx, int APAD) {
@@ -758,6 +758,9 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
   // k_tc; a service warp that also samples one cell behind the pipeline - its ~11 k instructions per tile slow the
   // two sub-partitions it shares and with them the whole barrier-coupled pipeline.)
   constexpr bool kJit = N > 3;
+  // two-head actors of small teams (simple_reference, A = 5 + 10): the exchange buffer does not fit into shared memory
+  // any more, so the OTHER warpgroup's shares travel through the scratch rows as well (the own shares stay in registers)
+  constexpr bool kXs = !kJit && APAD > 8;
   static_assert(!(kJit && FUSED), "the fused World.step keeps every agent of a row in registers: teams of <= 3");
   extern __shared__ __align__(128) unsigned char smem[];
 #ifdef MPE_TC_PHASES
@@ -941,11 +944,11 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
     const float *w2f = reinterpret_cast<const float *>(sm_w + w.off_w2f);
     unsigned char *own_x = tile_smem(own), *own_h = own_x + xb;
     uint8_t *own_act = own_h + 16384;
-    const f2 *own_xchg2 = reinterpret_cast<const f2 *>(own_act + (kRows * N * 2 + 127) / 128 * 128);
+    [[maybe_unused]] const f2 *own_xchg2 = reinterpret_cast<const f2 *>(own_act + (kRows * N * 2 + 127) / 128 * 128);
     float *stage_obs = reinterpret_cast<float *>(own_x), *stage_rew = stage_obs + kRows * R;
     uint32_t ph_d1[2] = {0, 0}, ph_g[2] = {0, 0};
     // large teams: this CTA's dense2-share scratch, [tile][half][cell][pair of head entries][row]
-    f2 *scr = kJit ? reinterpret_cast<f2 *>(w.scratch) + (size_t)blockIdx.x * tc2_scratch_f2_per_cta(N, APAD) : nullptr;
+    f2 *scr = (kJit || kXs) ? reinterpret_cast<f2 *>(w.scratch) + (size_t)blockIdx.x * tc2_scratch_f2_per_cta(N, APAD) : nullptr;
     mbar_wait(&bars[0], 0);
 #ifdef MPE_TC_PHASES
     if (dbg && tid == 0 && blockIdx.x < 148) g_tc_timeline[blockIdx.x * 128 + 67] = clock64();
@@ -1098,6 +1101,10 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
 #pragma unroll
                 for (int a = 0; a < APAD / 2; ++a) lgp[tt][a] = add2(lgp[tt][a], pl[a]);
               }
+          } else if constexpr (kXs) {  // the other tile's rows: one scratch row per cell, summed by the owner
+            f2 *dst = scr + ((size_t)((X * 2 + half) * 2 * N + k) * (APAD / 2)) * kRows + row;
+#pragma unroll
+            for (int a = 0; a < APAD / 2; ++a) dst[a * kRows] = pl[a];
           } else {  // the other tile's rows: park this warpgroup's share for its owner (store, then add)
             f2 *xr = reinterpret_cast<f2 *>(tile_smem(X) + xb + 16384 + (kRows * N * 2 + 127) / 128 * 128) +
                      (size_t)t * (APAD / 2) * kRows + row;
@@ -1291,7 +1298,17 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
             float lgt[APAD];
 #pragma unroll
             for (int a = 0; a < APAD / 2; ++a)
-              upk(add2(lgp[t][a], own_xchg2[((size_t)t * (APAD / 2) + a) * kRows + row]), lgt[2 * a], lgt[2 * a + 1]);
+            {
+              f2 other;
+              if constexpr (kXs) {
+                const f2 *sf = scr + ((size_t)((own * 2 + (1 - half)) * 2 * N + t) * (APAD / 2) + a) * kRows + row;
+                const f2 *sb = scr + ((size_t)((own * 2 + (1 - half)) * 2 * N + (2 * N - 1 - t)) * (APAD / 2) + a) * kRows + row;
+                other = add2(*sf, *sb);
+              } else {
+                other = own_xchg2[((size_t)t * (APAD / 2) + a) * kRows + row];
+              }
+              upk(add2(lgp[t][a], other), lgt[2 * a], lgt[2 * a + 1]);
+            }
             const int64_t orow = b * N + t;
 #pragma unroll
             for (int a = 0; a < APAD; ++a) z[a] = a < w.A ? lgt[a] + gn[t][a] : 0.0f;
