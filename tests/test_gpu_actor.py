@@ -190,23 +190,64 @@ def test_host_buffer_acting_matches_device_acting():
     assert np.array_equal(au, dev['act_u'].cpu().numpy()) and np.array_equal(oh, dev['onehot'].cpu().numpy())
 
 
-def test_tensor_core_and_simt_paths_agree():
-    """Same weights, same injected noise: logits within 1e-5, sampled indices equal outside the gap band."""
+@pytest.mark.parametrize('N,D,A,B', [(3, 10, 5, 33_000), (2, 21, [5, 10], 9_000), (2, 11, 5, 4_100),
+                                     (4, 12, 5, 3_000), (6, 16, 5, 5_000), (9, 22, 5, 2_100), (12, 28, 5, 1_537)])
+def test_tensor_core_and_simt_paths_agree(N, D, A, B):
+    """Same weights, same injected noise: logits within 1e-5, sampled indices equal outside the gap band - for
+    every team size / head layout the tensor-core kernel covers (resident operands, operand ring + scratch shares,
+    two heads through scratch rows), at batch sizes that are not multiples of the 128-env tile."""
     import multiagent_rl_b200 as m
-    sd = actor_ref.init_state_dict(10, 5, 11)
+    sd = actor_ref.init_state_dict(D, A, 11)
     for k in sd:  # larger weights (trained policies are sharper than the default init)
         sd[k] = sd[k] * 2.0
-    B = 33_000
+    width = sum(A) if isinstance(A, list) else A
+    a0 = A[0] if isinstance(A, list) else A
     rng = np.random.RandomState(3)
-    obs = rng.uniform(-2, 2, (B, 3, 10)).astype(np.float32)
-    gum = -np.log(-np.log(rng.uniform(1e-6, 1 - 1e-6, (B, 3, 5)))).astype(np.float32)
+    obs = rng.uniform(-2, 2, (B, N, D)).astype(np.float32)
+    gum = -np.log(-np.log(rng.uniform(1e-6, 1 - 1e-6, (B, N, width)))).astype(np.float32)
     outs = {}
     for impl in ('simt', 'tc'):
         a = m.FusedActor(sd, impl=impl)
         outs[impl] = a.forward(torch.from_numpy(obs), gumbel=gum, want_logits=True)
+        nolog = a.forward(torch.from_numpy(obs), gumbel=gum)  # the path that does not materialise the logits
+        same = nolog['act_u'].cpu().numpy() == outs[impl]['act_u'].cpu().numpy()
+        want = np.concatenate(actor_ref.forward(sd, obs)['logits'], -1)
+        assert np.all(same | (actor_ref.top2_gap(want[..., :a0], gum[..., :a0]) < GAP))
     ls, lt = outs['simt']['logits'].cpu().numpy(), outs['tc']['logits'].cpu().numpy()
-    want = actor_ref.forward(sd, obs)['logits'][0]
     assert np.abs(ls - want).max() <= LOGIT_ATOL and np.abs(lt - want).max() <= LOGIT_ATOL
-    gap = actor_ref.top2_gap(want, gum)
+    gap = actor_ref.top2_gap(want[..., :a0], gum[..., :a0])
     same = outs['simt']['act_u'].cpu().numpy() == outs['tc']['act_u'].cpu().numpy()
     assert np.all(same | (gap < GAP))
+    if isinstance(A, list):
+        gap = actor_ref.top2_gap(want[..., a0:], gum[..., a0:])
+        same = outs['simt']['act_c'].cpu().numpy() == outs['tc']['act_c'].cpu().numpy()
+        assert np.all(same | (gap < GAP))
+
+
+@pytest.mark.parametrize('impl,N', [('tc', 3), ('tc', 6), ('simt', 3)])
+def test_sampler_draws_from_softmax_of_the_logits(impl, N):
+    """F.gumbel_softmax(hard=True) draws index a with probability softmax(logits)[a]
+    (rls/agent/multiagent/ddpg_gumbel_fix.py:109-116).  262,144 rows with the SAME observation, Philox noise keyed by
+    the row: the empirical action frequencies of every agent must match softmax(logits) within 5 sigma, and two
+    different steps must be (nearly) independent draws."""
+    import multiagent_rl_b200 as m
+    D = 4 + 2 * N
+    sd = actor_ref.init_state_dict(D, 5, 21)
+    for k in sd:
+        if 'dense2' in k:
+            sd[k] = sd[k] * 6.0
+    B = 1 << 18
+    one = np.random.RandomState(5).uniform(-1, 1, (1, N, D)).astype(np.float32)
+    obs = torch.from_numpy(np.repeat(one, B, 0))
+    actor = m.FusedActor(sd, seed=99, impl=impl)
+    lg = actor_ref.forward(sd, one)['logits'][0][0].astype(np.float64)  # [N, 5]
+    p = np.exp(lg - lg.max(-1, keepdims=True))
+    p /= p.sum(-1, keepdims=True)
+    a1 = actor.forward(obs, step=7)['act_u'].cpu().numpy()
+    a2 = actor.forward(obs, step=8)['act_u'].cpu().numpy()
+    for t in range(N):
+        freq = np.bincount(a1[:, t], minlength=5) / B
+        sigma = np.sqrt(p[t] * (1 - p[t]) / B)
+        assert np.all(np.abs(freq - p[t]) <= 5 * sigma + 1e-6), (t, freq, p[t])
+        agree = (a1[:, t] == a2[:, t]).mean()  # independent draws agree with probability sum p^2
+        assert abs(agree - (p[t] ** 2).sum()) < 0.01
