@@ -13,7 +13,8 @@ from .env import BatchedMultiAgentEnv, make_env  # noqa: F401
 from .actor import ActingTrainer, FusedActingMixin, FusedActor  # noqa: F401
 from .networks import ActorNetwork  # noqa: F401
 from .replay import DeviceReplayBuffer  # noqa: F401
+from .history import EpisodeHistory  # noqa: F401
 from . import distributed  # noqa: F401
 
 __all__ = ['make_env', 'BatchedMultiAgentEnv', 'FusedActor', 'FusedActingMixin', 'ActingTrainer',
-           'ActorNetwork', 'DeviceReplayBuffer', 'distributed']
+           'ActorNetwork', 'DeviceReplayBuffer', 'EpisodeHistory', 'distributed']

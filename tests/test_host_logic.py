@@ -97,3 +97,45 @@ def test_golden_actor_loads_into_torch_mirror(golden_dir):
     with torch.no_grad():
         out = net(torch.from_numpy(g['obs'].astype(np.float32)))
     assert np.max(np.abs(out.numpy() - g['logits0'])) < 1e-6
+
+
+def test_episode_history_matches_the_reference_bookkeeping(tmp_path):
+    """experiments/run.py:23-25,55-57,62-65,94-100 run by hand on one env == EpisodeHistory on a batch of envs,
+    column by column; the pickle has the keys reward_plot*.py / reward_test_phase_csv.py read."""
+    import pickle
+    from multiagent_rl_b200.history import EpisodeHistory
+    B, N, L, T = 3, 3, 5, 17
+    rng = np.random.RandomState(0)
+    rew = rng.normal(size=(T, B, N))
+    # the reference loop, once per env
+    want = []
+    for b in range(B):
+        episode_rewards, agent_rewards, step = [0.0], [[0.0] for _ in range(N)], 0
+        for t in range(T):
+            for i in range(N):
+                episode_rewards[-1] += rew[t, b, i]
+                agent_rewards[i][-1] += rew[t, b, i]
+            step += 1
+            if step >= L:
+                step = 0
+                episode_rewards.append(0)
+                for a in agent_rewards:
+                    a.append(0)
+        want.append((episode_rewards, agent_rewards))
+    h = EpisodeHistory(B, N, max_episode_len=L)
+    h.add_rollout(torch.from_numpy(rew[:9]))
+    for t in range(9, T):
+        h.add_step(torch.from_numpy(rew[t]))
+    hist = h.history(order='env')
+    E = T // L
+    for b in range(B):
+        assert np.allclose(hist['reward_episodes'][b * E:(b + 1) * E], want[b][0][:E], atol=1e-12)
+        for i in range(N):
+            assert np.allclose(hist['reward_episodes_by_agents'][i][b * E:(b + 1) * E], want[b][1][i][:E], atol=1e-12)
+    # trailing in-progress entry = env 0's partial episode, as the reference's lists end
+    assert np.isclose(hist['reward_episodes'][-1], want[0][0][-1])
+    path = h.save(str(tmp_path / 'history_simple_spread_0.pkl'))
+    with open(path, 'rb') as fp:
+        back = pickle.load(fp)
+    assert set(back) == {'reward_episodes', 'reward_episodes_by_agents'} and len(back['reward_episodes_by_agents']) == N
+    assert len(back['reward_episodes']) == B * E + 1
