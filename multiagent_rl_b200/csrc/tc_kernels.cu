@@ -217,10 +217,11 @@ __device__ __forceinline__ f2 rcp2_newton(f2 d) {
 // [i_a i_b f_a f_b g_a g_b o_a o_b] per pair of units (a, b) = (2p, 2p+1), so that the two cells of a pair sit in
 // adjacent registers and every FP32 operation of the cell is one FFMA2/FADD2/FMUL2.  bg = 32 biases in the same
 // order, pre-multiplied by -log2(e) (x2 for the g gate); c = the 4 packed cell-state pairs; pl = packed dense2
-// partial sums.  The MUFU pipe is the floor of this kernel, so the cell is arranged to need 6 MUFU ops (5 ex2 +
-// 1 rcp) instead of the textbook 10: with e* = exp(-x) (arguments clamped so that no product overflows)
-//   c' = sigmoid(f) c + sigmoid(i) tanh(g) = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ef)(1+ei)(1+eg)]   one rcp
-//   h  = sigmoid(o) tanh(c') = (1 - ec) / ((1+eo)(1+ec))          reciprocal by Newton iteration on the FMA pipe
+// partial sums.  The MUFU pipe is the floor of this kernel, so the cell is arranged to need 5 MUFU ops (the five
+// ex2) instead of the textbook 10: with e* = exp(-x) (arguments clamped so that no product overflows)
+//   c' = sigmoid(f) c + sigmoid(i) tanh(g) = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ef)(1+ei)(1+eg)]   one reciprocal
+//   h  = sigmoid(o) tanh(c') = (1 - ec) / ((1+eo)(1+ec))                                              one reciprocal
+// and both reciprocals (denominators >= 1) by a bit-trick seed + 3 Newton steps on the FMA pipe.
 // Writes h as an fp16 hi/lo K-chunk of the recurrent A operand when `store_h`.
 template <int APAD>
 __device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float *bg, const float *w2rows, f2 (&c)[4],
@@ -245,9 +246,7 @@ __device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float 
     upk(aO, x0, x1); const f2 eO = pk(ex2_approx(fminf(x0, kClamp)), ex2_approx(fminf(x1, kClamp)));
     const f2 F = add2(eF, ONE), P = mul2(add2(eI, ONE), add2(eG, ONE));
     const f2 num = fma2(c[p], P, mul2(fma2(eG, NEG1, ONE), F));
-    float d0, d1;
-    upk(mul2(F, P), d0, d1);
-    c[p] = mul2(num, pk(rcp_approx(d0), rcp_approx(d1)));
+    c[p] = mul2(num, rcp2_newton(mul2(F, P)));  // den >= 1: Newton on the FMA pipe (measured: -3 % kernel time vs MUFU.RCP)
     pO[p] = add2(eO, ONE);
   }
   // stage 2: h = sigmoid(o) tanh(c) = (1 - ec) / ((1 + eo)(1 + ec)), reciprocal on the FMA pipe
