@@ -212,7 +212,7 @@ def run_b200(args):
     import torch.distributed as dist
     import multiagent_rl_b200 as m
     from multiagent_rl_b200 import distributed as D
-    from oracle import actor_ref  # weights of the reference architecture, default-init distribution
+    from multiagent_rl_b200.networks import random_state_dict  # reference architecture, default-init distribution
 
     rank, world, local = D.init_from_env()
     if world != args.gpus:
@@ -224,7 +224,7 @@ def run_b200(args):
     pk = peaks()
 
     env = m.make_env(SCENARIO, num_envs=B, batched=True, seed=SEED, env_id_offset=off, max_episode_len=EP_LEN)
-    actor = m.FusedActor(actor_ref.init_state_dict(OBS_DIM, ACT_DIM, SEED), device=dev, seed=SEED)
+    actor = m.FusedActor(random_state_dict(OBS_DIM, ACT_DIM, SEED), device=dev, seed=SEED)
     env.reset()
     # per-step outputs of the fused kernel (what a replay writer consumes)
     obs_next = torch.empty((1, B, N_AGENTS, OBS_DIM), device=dev)

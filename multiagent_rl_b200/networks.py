@@ -47,3 +47,35 @@ class ActorNetwork(nn.Module):
         if self.model_head:
             return policy, self.dense3(hid)
         return policy
+
+
+def random_state_dict(D, A, seed, model_head=False):
+    """Random actor weights with torch's default-init distribution (U(-1/sqrt(fan_in), 1/sqrt(fan_in))) under the
+    reference's state_dict keys (rls/model/ac_network_multi_gumbel.py:24-50), drawn from numpy so that benchmarks and
+    profiling targets get the same weights on every box without touching torch's RNG.  A: int or [A0, A1]."""
+    import numpy as np
+    hid, h = 64, 32
+    rng = np.random.RandomState(seed)
+
+    def U(shape, fan):
+        b = 1.0 / np.sqrt(fan)
+        return rng.uniform(-b, b, size=shape).astype(np.float32)
+
+    sd = {'dense1.module.weight': U((hid, D), D), 'dense1.module.bias': U((hid,), D)}
+    for sfx in ('', '_reverse'):
+        sd['bilstm.weight_ih_l0' + sfx] = U((4 * h, hid), h)
+        sd['bilstm.weight_hh_l0' + sfx] = U((4 * h, h), h)
+        sd['bilstm.bias_ih_l0' + sfx] = U((4 * h,), h)
+        sd['bilstm.bias_hh_l0' + sfx] = U((4 * h,), h)
+    if isinstance(A, (list, tuple)):
+        sd['dense2_1.module.weight'] = U((A[0], hid), hid)
+        sd['dense2_1.module.bias'] = U((A[0],), hid)
+        sd['dense2_2.module.weight'] = U((A[1], hid), hid)
+        sd['dense2_2.module.bias'] = U((A[1],), hid)
+    else:
+        sd['dense2.module.weight'] = U((A, hid), hid)
+        sd['dense2.module.bias'] = U((A,), hid)
+    if model_head:
+        sd['dense3.module.weight'] = U((D, hid), hid)
+        sd['dense3.module.bias'] = U((D,), hid)
+    return sd

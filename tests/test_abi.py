@@ -75,3 +75,15 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
+
+
+def test_only_the_cpu_arms_of_the_bench_touch_the_oracle():
+    """tools/ and the B200 arm of bench.py take their synthetic weights from the package; bench.py imports the
+    oracle in exactly one place, the CPU loop that serves cpu_baseline and --impl reference."""
+    import glob
+    for f in glob.glob(os.path.join(ROOT, 'tools', '*.py')):
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', open(f).read(), flags=re.M), f
+    txt = open(os.path.join(ROOT, 'bench.py')).read()
+    hits = [m_.start() for m_ in re.finditer(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M)]
+    assert len(hits) == 1
+    assert txt.rfind('def cpu_loop', 0, hits[0]) > txt.rfind('def run_b200', 0, hits[0])

@@ -7,7 +7,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiagent_rl_b200 as m  # noqa: E402
-from oracle import actor_ref  # noqa: E402
+from multiagent_rl_b200.networks import random_state_dict  # noqa: E402
 
 CONFIGS = [('simple_spread', None, 65536), ('simple_spread', 6, 65536), ('simple_spread', 9, 32768),
            ('simple_spread', 12, 32768), ('simple_reference', None, 65536), ('simple_speaker_listener', None, 65536)]
@@ -16,7 +16,7 @@ CONFIGS += [(s, n, 1 << 20) for s, n, _ in CONFIGS]
 for scen, n, B in CONFIGS:
     env = m.make_env(scen, n=n, num_envs=B, batched=True, seed=1, max_episode_len=25)
     A = [5, 10] if scen == 'simple_reference' else 5
-    actor = m.FusedActor(actor_ref.init_state_dict(env.obs_dim, A, 1), seed=1)
+    actor = m.FusedActor(random_state_dict(env.obs_dim, A, 1), seed=1)
     env.reset()
     T = 25
     env.rollout(actor, T)

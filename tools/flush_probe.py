@@ -13,12 +13,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ['MPE_TC_TIMELINE'] = '1'
 import multiagent_rl_b200 as m  # noqa: E402
 from multiagent_rl_b200 import _lib  # noqa: E402
-from oracle import actor_ref  # noqa: E402
+from multiagent_rl_b200.networks import random_state_dict  # noqa: E402
 
 dev = torch.device('cuda:0')
 B = 65536
 env = m.make_env('simple_spread', num_envs=B, batched=True, seed=1)
-actor = m.FusedActor(actor_ref.init_state_dict(10, 5, 1), seed=1)
+actor = m.FusedActor(random_state_dict(10, 5, 1), seed=1)
 env.reset()
 wbuf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 rbuf = torch.zeros(64 << 20, dtype=torch.float32, device=dev)

@@ -8,11 +8,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiagent_rl_b200 as m  # noqa: E402
-from oracle import actor_ref  # noqa: E402
+from multiagent_rl_b200.networks import random_state_dict  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'all'
 dev = torch.device('cuda:0')
-actor = m.FusedActor(actor_ref.init_state_dict(10, 5, 12345678), device=dev, seed=1)
+actor = m.FusedActor(random_state_dict(10, 5, 12345678), device=dev, seed=1)
 if which in ('all', 'step'):
     B = 1 << 20
     env = m.make_env('simple_spread', num_envs=B, batched=True, seed=1)
@@ -35,7 +35,7 @@ if which in ('all', 'rollout', 'actor'):
             actor.forward(obs)
     torch.cuda.synchronize()
 if which in ('all', 'bign'):
-    actor6 = m.FusedActor(actor_ref.init_state_dict(16, 5, 1), device=dev, seed=1)
+    actor6 = m.FusedActor(random_state_dict(16, 5, 1), device=dev, seed=1)
     env6 = m.make_env('simple_spread', n=6, num_envs=65536, batched=True, seed=1)
     obs6 = env6.reset()
     for _ in range(3):

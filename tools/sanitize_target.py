@@ -8,7 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiagent_rl_b200 as m  # noqa: E402
-from oracle import actor_ref  # noqa: E402
+from multiagent_rl_b200.networks import random_state_dict  # noqa: E402
 
 for scen, n, B, A in [('simple_spread', None, 333, 5), ('simple_spread', 6, 70, 5), ('simple_spread', 9, 41, 5),
                       ('simple_spread', 12, 37, 5), ('simple_reference', None, 200, [5, 10]),
@@ -26,7 +26,7 @@ for scen, n, B, A in [('simple_spread', None, 333, 5), ('simple_spread', 6, 70, 
     env = m.make_env(scen, n=n, num_envs=B, batched=True, seed=3, max_episode_len=3)
     obs = env.reset()
     for impl in (['simt', 'tc'] if env.n <= 3 else ['simt']):
-        actor = m.FusedActor(actor_ref.init_state_dict(env.obs_dim, A, 1), impl=impl)
+        actor = m.FusedActor(random_state_dict(env.obs_dim, A, 1), impl=impl)
         actor.forward(obs, want_logits=True, want_onehot=True)
         env.rollout(actor, 5, record=True)
         env.rollout(actor, 2)

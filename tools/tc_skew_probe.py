@@ -7,11 +7,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiagent_rl_b200 as m  # noqa: E402
-from oracle import actor_ref  # noqa: E402
+from multiagent_rl_b200.networks import random_state_dict  # noqa: E402
 
 B = 65536
 env = m.make_env('simple_spread', num_envs=B, batched=True, seed=1)
-actor = m.FusedActor(actor_ref.init_state_dict(10, 5, 1), seed=1)
+actor = m.FusedActor(random_state_dict(10, 5, 1), seed=1)
 env.reset()
 for skew in [int(x) for x in (sys.argv[1:] or ['0', '300', '600', '1000', '1500', '2000', '3000', '0'])]:
     os.environ['MPE_TC_SKEW'] = str(skew)

@@ -10,19 +10,19 @@ os.environ['MPE_TC_TIMELINE'] = '1'
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiagent_rl_b200 as m  # noqa: E402
 from multiagent_rl_b200 import _lib  # noqa: E402
-from oracle import actor_ref  # noqa: E402
+from multiagent_rl_b200.networks import random_state_dict  # noqa: E402
 
 B = 65536
 NAG = int(os.environ.get('TL_N', '3'))  # TL_N=6: actor-only timeline of the large-team path
 if NAG == 3:
     env = m.make_env('simple_spread', num_envs=B, batched=True, seed=1)
-    actor = m.FusedActor(actor_ref.init_state_dict(10, 5, 1), seed=1)
+    actor = m.FusedActor(random_state_dict(10, 5, 1), seed=1)
     env.reset()
     for _ in range(3):
         env.rollout(actor, 1, record=True)
 else:
     env = m.make_env('simple_spread', n=NAG, num_envs=B, batched=True, seed=1)
-    actor = m.FusedActor(actor_ref.init_state_dict(env.obs_dim, 5, 1), seed=1)
+    actor = m.FusedActor(random_state_dict(env.obs_dim, 5, 1), seed=1)
     obs = env.reset()
     for _ in range(3):
         actor.forward(obs)
