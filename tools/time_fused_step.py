@@ -1,5 +1,7 @@
-"""Experiment: de-phase the two warpgroups of k_tc2 (MPE_TC_SKEW = cycles warpgroup 1 waits before the cell
-pipeline) so that the two warps of an SM sub-partition do not hit their TMEM round trips at the same time."""
+"""Back-to-back timing of the fused step kernel (mpe_rollout, T=1, 65,536 envs, simple_spread N=3): no L2 flush, 200
+launches inside one CUDA-event pair, so launch latency and event overhead are amortised.  This is the number the
+kernel experiments in profiles/README.md are quoted in; bench.py's per-step event timing with an L2 flush in between
+comes out ~6 us higher.  A/B a variant build with MPE_B200_LIB=tmp_ab/libmpe_b200_<name>.so."""
 import os
 import sys
 
@@ -13,8 +15,7 @@ B = 65536
 env = m.make_env('simple_spread', num_envs=B, batched=True, seed=1)
 actor = m.FusedActor(random_state_dict(10, 5, 1), seed=1)
 env.reset()
-for skew in [int(x) for x in (sys.argv[1:] or ['0', '300', '600', '1000', '1500', '2000', '3000', '0'])]:
-    os.environ['MPE_TC_SKEW'] = str(skew)
+for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     for _ in range(20):
         env.rollout(actor, 1, record=True)
     torch.cuda.synchronize()
@@ -24,4 +25,4 @@ for skew in [int(x) for x in (sys.argv[1:] or ['0', '300', '600', '1000', '1500'
         env.rollout(actor, 1, record=True)
     e1.record()
     torch.cuda.synchronize()
-    print('skew %5d cycles: %.2f us per 65,536-env step (200 back-to-back launches)' % (skew, e0.elapsed_time(e1) * 5))
+    print('%.2f us per 65,536-env step (200 back-to-back launches)' % (e0.elapsed_time(e1) * 5))
