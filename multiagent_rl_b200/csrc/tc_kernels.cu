@@ -946,6 +946,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
     [[maybe_unused]] const f2 *own_xchg2 = reinterpret_cast<const f2 *>(own_act + (kRows * N * 2 + 127) / 128 * 128);
     float *stage_obs = reinterpret_cast<float *>(own_x), *stage_rew = stage_obs + kRows * R;
     uint32_t ph_d1[2] = {0, 0}, ph_g[2] = {0, 0};
+    bool tma_pending = false;  // row 0: a bulk store of the staging buffer (= the obs operand buffer) may still be reading it
     // large teams: this CTA's dense2-share scratch, [tile][half][cell][pair of head entries][row]
     f2 *scr = (kJit || kXs) ? reinterpret_cast<f2 *>(w.scratch) + (size_t)blockIdx.x * tc2_scratch_f2_per_cta(N, APAD) : nullptr;
     mbar_wait(&bars[0], 0);
@@ -977,6 +978,13 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
 #pragma unroll
                 for (int k = 0; k < 10; ++k) comm[i][k] = s.comm[((int64_t)i * 10 + k) * s.B + b];
             }
+          }
+          if (FUSED) {
+            // The previous step's TMA store drains the staging buffer while the state loads above are in flight;
+            // only now, before the operand stores reuse that memory, does its issuer wait for the read to finish.
+            if (tma_pending) bulk_wait_read_all();
+            tma_pending = false;
+            bar_sync_n(2 + own, 128);
           }
 #pragma unroll
           for (int t = 0; t < N; ++t) {
@@ -1420,7 +1428,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
             }
           }
           TL(half, 23);
-          if (row == 0 && tma_ok && (g_obs != nullptr || g_rew != nullptr)) bulk_wait_read_all();
+          if (row == 0 && tma_ok && (g_obs != nullptr || g_rew != nullptr)) tma_pending = true;
         } else {
           bar_sync_n(2 + own, 128);
           const int rows = valid * N;
@@ -1436,10 +1444,11 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
             }
         }
         TL(half, 30);
-        bar_sync_n(1, 256);  // staging (aliases x), exchange and action buffers of both tiles are free again
+        bar_sync_n(1, 256);  // exchange and action buffers of both tiles are free again (staging: see tma_pending)
         TL(half, 31);
       }
     }
+    if (tma_pending) bulk_wait_read_all();  // shared memory must stay valid until the last bulk store has read it
   }
   tc_fence_before();
   __syncthreads();
