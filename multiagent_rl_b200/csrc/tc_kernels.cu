@@ -1512,9 +1512,12 @@ bool tc_actor_supported(const TcDev &w, int N) {
   return tc_supported(w) && (N == 2 || N == 3 || ((N == 4 || N == 6 || N == 9 || N == 12) && w.scratch != nullptr));
 }
 bool tc_rollout_supported(const TcDev &w, int N) { return tc_supported(w) && (N == 2 || N == 3); }
-size_t tc_scratch_floats(int sm_count) {  // the larger of k_tc's forward shares and k_tc2's per-cell shares (N = 12, APAD = 16)
-  const size_t v1 = (size_t)sm_count * 2 * 12 * 16 * kRows, v2 = (size_t)sm_count * tc2_scratch_f2_per_cta(12, 16) * 2;
-  return v1 > v2 ? v1 : v2;
+size_t tc_scratch_floats(int sm_count) {
+  // the largest of: k_tc's forward shares; k_tc2's per-cell shares for the instantiated large teams (N <= 12, one head
+  // of <= 8 entries) and for the two-head small teams (N <= 3, 16 entries)
+  const size_t v1 = (size_t)sm_count * 2 * 12 * 16 * kRows;
+  const size_t v2 = (size_t)sm_count * tc2_scratch_f2_per_cta(12, 8) * 2, v3 = (size_t)sm_count * tc2_scratch_f2_per_cta(3, 16) * 2;
+  return v1 > v2 ? (v1 > v3 ? v1 : v3) : (v2 > v3 ? v2 : v3);
 }
 
 cudaError_t launch_actor_forward_tc(const TcDev &w, const ActorIO &io, cudaStream_t st) {
