@@ -25,11 +25,19 @@ struct GroupLayout {
   static constexpr int LANES = EPW * G; // active lanes
   static constexpr int D = 4 + 2 * N;
   static constexpr int R = N * D;
-  // Staging rows: when an env's R obs values are a multiple of 16 B, every env gets its own TMA bulk store and
-  // the rows are padded by 16 B so that the lanes of different envs hit different shared-memory banks
-  // (R = 96 or 336 floats would otherwise put every env on the same bank: 16-way conflicts).
-  static constexpr bool kPerEnv = (R * (int)sizeof(T)) % 16 == 0;
-  static constexpr int RS = kPerEnv ? R + 16 / (int)sizeof(T) : R;
+  // Staging rows.  The fp32 build writes them with the widest vector the row length allows (float4 when D % 4 == 0,
+  // else float2) and picks the row stride RS so that the lanes of one shared-memory wavefront (8 lanes for 16 B
+  // stores, 16 for 8 B) start in different banks: lane (env el, part q) starts at el * RS + q * A * D floats, i.e.
+  //   N = 6  (G 2, D 16, R  96): 16 B slot index (RS/4) el + 12 q -> RS = 100 gives el + 4 q: 0..7 distinct
+  //   N = 9  (G 3, D 22, R 198):  8 B slot index  99 el + 33 q = 3 el + q (mod 16): distinct, no padding
+  //   N = 12 (G 4, D 28, R 336): 16 B slot index  84 el + 21 q = 4 el + 5 q (mod 8): distinct, no padding
+  // A padded stride means one TMA bulk store per env (kPerEnv), an unpadded one a single store for the warp's span.
+  // The fp64 validation build keeps scalar stores and the 16 B pad.
+  static constexpr bool kF32 = sizeof(T) == 4;
+  static constexpr int kVec = kF32 ? (D % 4 == 0 ? 4 : 2) : 1;
+  static constexpr int kPad = kF32 ? (N == 6 ? 4 : 0) : ((R * (int)sizeof(T)) % 16 == 0 ? 16 / (int)sizeof(T) : 0);
+  static constexpr bool kPerEnv = kPad != 0;
+  static constexpr int RS = R + kPad;
   static constexpr int kWarpBytes = ((EPW * RS + EPW * N) * (int)sizeof(T) + 127) / 128 * 128;
   static constexpr int kBlockBytes = kWarpBytes * (kStepThreads / 32);
   static_assert(N % G == 0, "agents must split evenly over the lanes of an env");
@@ -63,7 +71,46 @@ __device__ __forceinline__ bool grp_emit(const GroupLanes<T, N, G> &g, const T (
                        (GL::kPerEnv || (EPW * R * sizeof(T)) % 16 == 0);
   const bool rew_tma = full && rew != nullptr && (reinterpret_cast<uintptr_t>(rew + b0 * N) & 15) == 0 &&
                        ((EPW * N * sizeof(T)) % 16 == 0);
-  if (obs != nullptr) {
+  if (obs != nullptr && obs_tma && GL::kVec > 1) {
+    // shared-memory staging with vector stores (the pointer is derived from the shared array only, so these are STS)
+    float *rowbase = reinterpret_cast<float *>(smem + warp * GL::kWarpBytes) + el * RS + q * A * D;
+    if (lane_ok) {
+#pragma unroll
+      for (int k = 0; k < A; ++k) {
+        if (GL::kVec == 4) {
+          *reinterpret_cast<float4 *>(rowbase + k * D) = make_float4((float)vx[k], (float)vy[k], (float)px[k], (float)py[k]);
+        } else {
+          *reinterpret_cast<float2 *>(rowbase + k * D) = make_float2((float)vx[k], (float)vy[k]);
+          *reinterpret_cast<float2 *>(rowbase + k * D + 2) = make_float2((float)px[k], (float)py[k]);
+        }
+      }
+    }
+    if (GL::kVec == 4) {
+#pragma unroll
+      for (int l = 0; l < L; l += 2) {
+        const T ax = __shfl_sync(FULL, lx[l % A], base_lane + l / A), ay = __shfl_sync(FULL, ly[l % A], base_lane + l / A);
+        const T bx = __shfl_sync(FULL, lx[(l + 1) % A], base_lane + (l + 1) / A);
+        const T by = __shfl_sync(FULL, ly[(l + 1) % A], base_lane + (l + 1) / A);
+        if (lane_ok) {
+#pragma unroll
+          for (int k = 0; k < A; ++k)
+            *reinterpret_cast<float4 *>(rowbase + k * D + 4 + 2 * l) =
+                make_float4((float)(ax - px[k]), (float)(ay - py[k]), (float)(bx - px[k]), (float)(by - py[k]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        const T llx = __shfl_sync(FULL, lx[l % A], base_lane + l / A);
+        const T lly = __shfl_sync(FULL, ly[l % A], base_lane + l / A);
+        if (lane_ok) {
+#pragma unroll
+          for (int k = 0; k < A; ++k)
+            *reinterpret_cast<float2 *>(rowbase + k * D + 4 + 2 * l) = make_float2((float)(llx - px[k]), (float)(lly - py[k]));
+        }
+      }
+    }
+  } else if (obs != nullptr) {
     T *rowbase = obs_tma ? st_obs + el * RS : obs + b * R;
     const bool wr = obs_tma ? lane_ok : active;
     if (wr) {
@@ -119,7 +166,7 @@ __global__ void __launch_bounds__(kStepThreads)
     k_step_grp(EnvState<T> s, const int32_t *__restrict__ act_u, T *__restrict__ obs, T *__restrict__ rew,
                uint8_t *__restrict__ done, int32_t *__restrict__ info_i, T *__restrict__ info_f) {
   using GL = GroupLayout<T, N, G>;
-  constexpr int A = GL::A, EPW = GL::EPW, D = GL::D, R = GL::R, L = N;
+  constexpr int A = GL::A, EPW = GL::EPW, L = N;
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int el = lane / G, q = lane - el * G;            // env within the warp, lane within the env
