@@ -251,3 +251,41 @@ def test_sampler_draws_from_softmax_of_the_logits(impl, N):
         assert np.all(np.abs(freq - p[t]) <= 5 * sigma + 1e-6), (t, freq, p[t])
         agree = (a1[:, t] == a2[:, t]).mean()  # independent draws agree with probability sum p^2
         assert abs(agree - (p[t] ** 2).sum()) < 0.01
+
+
+@pytest.mark.parametrize('B', [65_536, 1 << 20])
+def test_fused_rollout_full_size_properties(B):
+    """BASELINE sizes (the bench's 65,536 envs and the north-star's 1,048,576): size-independent invariants of the
+    fused kernel's recorded transitions instead of the oracle -
+      * rewards are what the float64 reward formula gives on the recorded next observations (nearest-agent
+        distance per landmark, -1 per agent within 0.30 including itself);
+      * the recorded velocity/position pair obeys integrate_state: pos' - pos = 0.1 vel' (from consecutive records);
+      * momentum: sum_i vel'_i = 0.75 sum_i vel_i + 0.1 sum_i u(action_i) (pair forces cancel);
+      * every action is drawn, Philox draws differ from step to step."""
+    import multiagent_rl_b200 as m
+    sd = actor_ref.init_state_dict(10, 5, 33)
+    actor = m.FusedActor(sd, seed=12)
+    env = m.make_env('simple_spread', num_envs=B, batched=True, seed=12, max_episode_len=25)
+    env.reset()
+    T = 3
+    obs, rew, act_u, _ = env.rollout(actor, T, step0=5, record=True)  # [T,B,N,D], [T,B,N], [T,B,N]
+    table = torch.tensor([[0, 0], [5, 0], [-5, 0], [0, 5], [0, -5]], dtype=torch.float64, device='cuda')
+    for t in range(T):
+        o = obs[t].double()
+        vel, pos = o[:, :, 0:2], o[:, :, 2:4]
+        lm = pos[:, 0:1, None, :] + o[:, 0:1, 4:].reshape(B, 1, 3, 2)          # landmarks from agent 0's relative rows
+        d = (pos[:, :, None, :] - lm).norm(dim=-1)                               # [B, agent, landmark]
+        base = -d.min(dim=1).values.sum(-1)                                      # -sum_l min_a dist
+        dd = (pos[:, :, None, :] - pos[:, None, :, :]).norm(dim=-1)              # [B, i, j], diagonal 0
+        coll = (dd < 0.30).sum(-1).double()
+        want = base[:, None] - coll
+        near = ((dd - 0.30).abs() < 1e-5).any(-1)                                # fp32 vs fp64 flag flips at the threshold
+        assert float(((rew[t].double() - want).abs() * (~near)).max()) < 2e-4
+        if t > 0:
+            prev = obs[t - 1].double()
+            assert float((pos - prev[:, :, 2:4] - 0.1 * vel).abs().max()) < 1e-6
+            u = table[act_u[t].long()].sum(1)
+            assert float((vel.sum(1) - 0.75 * prev[:, :, 0:2].sum(1) - 0.1 * u).abs().max()) < 1e-4
+    a = act_u.reshape(-1)
+    assert int(a.min()) == 0 and int(a.max()) == 4 and len(torch.unique(a)) == 5
+    assert float((act_u[0] != act_u[1]).float().mean()) > 0.2
