@@ -158,7 +158,9 @@ enum { B_X = 0, B_D1, B_H1, B_G, B_H, B_PER_WG };
 
 // observation A operands: all N agents resident for N <= 3; for larger teams a double buffer that is refilled just
 // in time, one cell ahead of the dense1 GEMM that consumes it
-__host__ __device__ inline int tc_x_slots(int N) { return N <= 3 ? N : 2; }
+// operand buffers: all agents resident (N <= 3); a ring of 4 (teams of 4 / 6: 16-wide operands, shared memory to
+// spare) or 2 (9 / 12 agents: 32-wide operands) buffers refilled ahead of the dense1 GEMMs
+__host__ __device__ constexpr int tc_x_slots(int N) { return N <= 3 ? N : (N <= 6 ? 4 : 2); }
 __host__ __device__ inline size_t tc_x_bytes(int N, int Kx) { return (size_t)tc_x_slots(N) * 2 * (Kx / 8) * kChunkA; }
 __host__ __device__ inline size_t tc_smem_bytes(uint32_t wbytes, int N, int Kx) {
   // weight image + per warpgroup: obs operands, recurrent h operand (hi/lo), action indices; + barriers
@@ -737,7 +739,7 @@ __host__ __device__ inline size_t tc2_tile_bytes(int N, int Kx, int APAD) {
   // larger teams and the two-head simple_reference actor keep the dense2 shares in the global scratch instead
   return tc_x_bytes(N, Kx) + 16384 + (size_t)((kRows * N * 2 + 127) / 128 * 128) + (N <= 3 && APAD <= 8 ? (size_t)N * APAD * kRows * 4 : 0);
 }
-enum { B2_XR = 0, B2_XF = 2, B2_EXTRA = 4 };  // per tile: obs operand buffer 0/1 ready, buffer 0/1 free again
+enum { B2_XR = 0, B2_XF = 4, B2_EXTRA = 8 };  // per tile: operand ring buffer q (< 4) ready / free again
 __host__ __device__ inline size_t tc2_smem_bytes(uint32_t wbytes, int N, int Kx, int APAD) {
   return (size_t)wbytes + 2 * tc2_tile_bytes(N, Kx, APAD) + (1 + 2 * B_PER_WG + 2 * B2_EXTRA) * 8 + 64;
 }
@@ -750,7 +752,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
     k_tc2(EnvState<float> s, TcDev w, ActorIO io, RolloutIO ro, int max_episode_len, int64_t ntiles, int dbg) {
   // Large teams (N > 3, actor only): the obs operands do not fit next to the weights, so a per-tile OPERAND WARP
   // (warps 10 / 11; the register file is allocated for 12 warps anyway) streams them from the caller's tensor into a
-  // two-deep operand ring one or two cells ahead of the dense1 GEMMs, and every cell's dense2 share goes to its own
+  // operand ring (4 buffers for 4 / 6 agents, 2 for 9 / 12) ahead of the dense1 GEMMs, and every cell's dense2 share goes to its own
   // global scratch row (L2 resident) from which the owner warpgroup completes the logits and samples after the
   // pipeline.  Inside the pipeline the eight epilogue warps do nothing but the dense1 epilogue and the cell math.
   // (Measured alternatives: refilling from the epilogue warps - 400 B of spills and exposed load latency, slower than
@@ -792,7 +794,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
       mbar_init(&bb[B_H1], 256);  // both warpgroups converted their half of h1
       mbar_init(&bb[B_G], 1);
       mbar_init(&bb[B_H], 256);   // both warpgroups finished their half of the cell
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < 4; ++q) {
         mbar_init(&xbars[g * B2_EXTRA + B2_XR + q], 32);  // the service warp filled operand buffer q
         mbar_init(&xbars[g * B2_EXTRA + B2_XF + q], 1);   // the dense1 GEMM reading buffer q has completed
       }
@@ -817,8 +819,9 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
   auto slot_col = [](int t) { return 128u + 64u * (uint32_t)(t & 1); };
   const int64_t npairs = (ntiles + 1) / 2;
   // large teams: index of cell j in the sequence of cells that have a dense1 GEMM (the two resident backward cells
-  // N, N+1 are skipped); the operand ring buffer of that GEMM is (index & 1)
+  // N, N+1 are skipped); the operand ring buffer of that GEMM is (index mod ring depth)
   auto d1_index = [](int j) { return j < N ? j : j - 2; };
+  constexpr int kRing = kJit ? tc_x_slots(N) : 1;  // power of two
 
   if (kJit && warp >= 10) {
     // =============================== operand warp of tile X = warp - 10 (large teams) ===============================
@@ -836,7 +839,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
 #pragma unroll 1
       for (int j = 0; j < 2 * N; ++j) {
         if (!need_e1(j)) continue;
-        const int t = agent_of(j), q = d1_index(j) & 1;
+        const int t = agent_of(j), q = d1_index(j) & (kRing - 1);
         if ((filled >> q) & 1u) { mbar_wait(&xb2[B2_XF + q], (ph_xf >> q) & 1u); ph_xf ^= 1u << q; }
         filled |= 1u << q;
         unsigned char *xh = sm_x + (size_t)(q * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
@@ -899,9 +902,9 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
             tc_fence_after();
           }
           // dense1 GEMM of cell j -> the agent's h1 slot.  Small teams: operand buffer = agent (all resident).
-          // Large teams: ring buffer (dense1 index & 1), filled by the service warp; its completion frees the buffer.
+          // Large teams: ring buffer (dense1 index mod depth), filled by the operand warp; its completion frees the buffer.
           auto dense1_cell = [&](int j) {
-            const int t = agent_of(j), q = d1_index(j) & 1, xs = kJit ? q : t;
+            const int t = agent_of(j), q = d1_index(j) & (kRing - 1), xs = kJit ? q : t;
             if constexpr (kJit) {
               mbar_wait(&xb2[B2_XR + q], (ph_xr >> q) & 1u); ph_xr ^= 1u << q;
               tc_fence_after();
