@@ -376,6 +376,29 @@ def side_measurements(m, actor, dev, pk, off):
     s = e0.elapsed_time(e1) * 1e-3 / 5
     out['actor_forward_only'] = {'envs': 262144, 'agent_steps_per_s': 262144 * N_AGENTS / s,
                                  'tflops': 262144 * FLOPS_PER_ENV_STEP / s / 1e12}
+    # the fused step at the north-star size (>= 1M envs per GPU): 4,096 tile pairs per launch, so the 13.5 % tail of
+    # the 65,536-env launch (256 pairs on 148 SMs) is gone; 240 MB of state + outputs per launch > L2, no flush needed
+    env.reset()
+    rec = (torch.empty((1, B, N_AGENTS, OBS_DIM), device=dev), torch.empty((1, B, N_AGENTS), device=dev),
+           torch.empty((1, B, N_AGENTS), dtype=torch.int32, device=dev))
+    from multiagent_rl_b200 import _lib
+    lib = _lib.load()
+
+    def fused(t):
+        _lib.check(lib.mpe_rollout(env._h, actor._h, 1, t, _lib.ptr(rec[0]), _lib.ptr(rec[1]), _lib.ptr(rec[2]), None,
+                                   _lib.current_stream(dev)), 'mpe_rollout')
+    for t in range(3):
+        fused(t)
+    torch.cuda.synchronize()
+    e0.record()
+    for t in range(20):
+        fused(3 + t)
+    e1.record()
+    torch.cuda.synchronize()
+    s = e0.elapsed_time(e1) * 1e-3 / 20
+    out['fused_step_1m_envs'] = {'envs': B, 'ms_per_step': s * 1e3, 'agent_steps_per_s': B * N_AGENTS / s,
+                                 'tflops': B * FLOPS_PER_ENV_STEP / s / 1e12,
+                                 'frac_of_bf16_sustained': B * FLOPS_PER_ENV_STEP / s / 1e12 / pk['bf16_tflops_sustained']}
     del env
     sys.path.insert(0, os.path.join(ROOT, 'tools'))
     import bench_env_configs
