@@ -26,6 +26,9 @@ SEED = 12345678  # main.py:41
 # algorithmic bytes of one env step: 41N + 8L + 4ND with N = L = 3, D = 10
 BYTES_PER_ENV_STEP = 41 * 3 + 8 * 3 + 4 * 3 * 10
 # algorithmic FLOPs of one actor forward per env: N (128 D + 49152 + 128 A)
+# DRAM traffic per launch of the two kernels the rooflines are quoted for, from the committed ncu --set full captures
+NCU_DRAM_BYTES_FUSED = 5.455e6   # k_tc2<0,3,1,8>, 65,536 envs: 5.455 MB read + 0 written (outputs stay in the 126 MB L2)
+NCU_DRAM_BYTES_STEP = 221.9e6    # k_step<float,0,3>, 1,048,576 envs: 88.1 MB read + 133.8 MB written (algorithmic 280 MB)
 FLOPS_PER_ENV_STEP = N_AGENTS * (128 * OBS_DIM + 49152 + 128 * ACT_DIM)
 FP32_SIMT_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # FFMA peak at max clock (not a measured number)
 
@@ -322,7 +325,10 @@ def run_b200(args):
                    'envs_per_gpu': B, 'l2': 'flushed between timed iterations (256 MiB memset outside the events)',
                    'actor_weights': 'random init, reference architecture (26,117 params)', 'seed': SEED},
         'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': pk['bf16_tflops_sustained'],
-                     'unit': 'TFLOP/s', 'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': None,
+                     'unit': 'TFLOP/s', 'frac': tflops / pk['bf16_tflops_sustained'],
+                     'traffic': NCU_DRAM_BYTES_FUSED if B == 65536 else None,
+                     'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch at 65,536 envs, '
+                                       'profiles/r1_ncu_full_summary_v8.txt (state + weights in, outputs stay in L2)',
                      'kernel': 'k_tc2<simple_spread,3,fused> (tcgen05 kind::f16, fp16 hi/lo split operands, fp32 TMEM accum)',
                      'peak_source': pk['source'] + ' bf16 sustained',
                      'flops_per_env_step': FLOPS_PER_ENV_STEP,
@@ -361,7 +367,9 @@ def side_measurements(m, actor, dev, pk, off):
     s = e0.elapsed_time(e1) * 1e-3 / reps
     gbs = B * BYTES_PER_ENV_STEP / s / 1e9
     out['roofline_env_step'] = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                                'frac': gbs / pk['hbm_gbs'], 'traffic': None, 'kernel': 'k_step<float,simple_spread,3>',
+                                'frac': gbs / pk['hbm_gbs'], 'traffic': NCU_DRAM_BYTES_STEP,
+                                'traffic_source': 'profiles/r1_ncu_full_summary_v5.txt, 1,048,576 envs per launch',
+                                'kernel': 'k_step<float,simple_spread,3>',
                                 'envs': B, 'agent_steps_per_s': B * N_AGENTS / s, 'us_per_launch': s * 1e6,
                                 'bytes_per_env_step': BYTES_PER_ENV_STEP, 'peak_source': pk['source']}
     obs = bufs[0]
