@@ -308,3 +308,33 @@ def test_return_tracking_and_stats():
     assert float(alias[2]) == 0.0  # zero-copy view of the (now cleared) device statistics
     assert abs(s[0] - float(tot.sum())) < 1e-2 * B and abs(s[1] - float((tot ** 2).sum())) < 1e-1 * B
     assert env.read_stats()[2] == 0
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_coincident_agents_give_nan_like_upstream(precision):
+    """Upstream has no epsilon on the pair distance: two agents at the same point get 0/0 = NaN forces.
+    The kernels must reproduce that (same NaN pattern in state, observations and rewards as the loop oracle, which
+    keeps Python's `min` semantics for NaN distances) and must not contaminate other envs of the batch."""
+    import warnings
+    B = 64  # env 5 has agents 0 and 1 coincident; every other env is regular
+    rng = np.random.RandomState(4)
+    pos = rng.uniform(-1, 1, (B, 3, 2)); vel = rng.uniform(-0.2, 0.2, (B, 3, 2)); lm = rng.uniform(-1, 1, (B, 3, 2))
+    pos[5, 1] = pos[5, 0]
+    act = rng.randint(0, 5, (B, 3))
+    env = _mk('simple_spread', None, B, precision, seed=1)
+    env.reset()
+    env.set_state(torch.from_numpy(pos), torch.from_numpy(vel), torch.from_numpy(lm))
+    obs, rew, _, _ = env.step(torch.from_numpy(act.astype(np.int32)))
+    obs, rew = _np(obs), _np(rew)
+    o = mpe_ref.make_env('simple_spread')
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for b in (4, 5, 6):
+            mpe_ref.set_state(o, pos[b], vel[b], lm[b])
+            on, rn, _, _ = o.step([np.eye(5)[a] for a in act[b]])
+            on, rn = np.stack(on), np.array(rn, dtype=np.float64)
+            assert np.array_equal(np.isnan(on), np.isnan(obs[b])), b
+            assert np.array_equal(np.isnan(rn), np.isnan(rew[b])), b
+            tol = 1e-12 if precision == 'fp64' else 5e-5
+            assert np.nanmax(np.abs(on - obs[b])) <= tol and (np.all(np.isnan(rn)) or np.nanmax(np.abs(rn - rew[b])) <= 10 * tol)
+    assert np.isnan(obs[5]).any() and not np.isnan(np.delete(obs, 5, 0)).any() and not np.isnan(np.delete(rew, 5, 0)).any()
