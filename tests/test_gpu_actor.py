@@ -289,3 +289,26 @@ def test_fused_rollout_full_size_properties(B):
     a = act_u.reshape(-1)
     assert int(a.min()) == 0 and int(a.max()) == 4 and len(torch.unique(a)) == 5
     assert float((act_u[0] != act_u[1]).float().mean()) > 0.2
+
+
+@pytest.mark.parametrize('scenario,n,A', [('simple_spread', None, 5), ('simple_reference', None, [5, 10]),
+                                          ('simple_speaker_listener', None, 5), ('simple_spread', 6, 5)])
+def test_fused_rollout_equals_stepwise_path_tiny_batches(scenario, n, A):
+    """Batches of 1, 2 and 129 envs (one row of one tile, a tile pair whose second tile has one row): the rollout
+    (one kernel for small teams, actor + step kernels for large ones) equals the step-by-step calls bit for bit,
+    across auto-resets."""
+    import multiagent_rl_b200 as m
+    for B in (1, 2, 129):
+        env = m.make_env(scenario, n=n, num_envs=B, batched=True, seed=3, max_episode_len=4)
+        env2 = m.make_env(scenario, n=n, num_envs=B, batched=True, seed=3, max_episode_len=4)
+        actor = m.FusedActor(actor_ref.init_state_dict(env.obs_dim, A, 1), seed=3)  # the rollout draws with the env's seed
+        env.reset()
+        obs = env2.reset()
+        rec = env.rollout(actor, 9, step0=0, record=True)
+        for t in range(9):
+            out = actor.forward(obs, step=t)
+            assert torch.equal(out['act_u'], rec[2][t]), (B, t)
+            obs, rew, _, _ = env2.step(out['act_u'], out['act_c'])
+            assert torch.equal(obs, rec[0][t]) and torch.equal(rew, rec[1][t]), (B, t)
+            if (t + 1) % 4 == 0:
+                obs = env2.reset()
