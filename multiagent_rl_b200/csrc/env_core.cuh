@@ -145,10 +145,15 @@ __device__ __forceinline__ void contact_force(T dx, T dy, T d2, T dist_min, T &g
     // 3 MUFU ops (rsq, ex2, lg2) and ~12 FP32 ops, branch free: softplus(y) = max(y, 0) + log(1 + exp(-|y|)).
     // Far pairs give exp -> 0, log(1) = 0, i.e. exactly +-0 (the double build skips them with the same result);
     // coincident agents give NaN like upstream's 0/0.
-    const float rinv = rsqrtf(d2);
+    // raw MUFU forms: rsqrtf() / __expf() wrap the approx instructions in denormal-range handling (8 extra
+    // instructions per pair) that cannot matter here - d2 is either 0 (coincident: inf -> NaN, as wanted) or far
+    // above 2^-126, and exp results below 2^-126 vanish in the 1 + e that follows either way
+    float rinv, e;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d2));
     const float dist = d2 * rinv;
     const float y = (dist_min - dist) * 1000.0f;  // -(dist - dist_min) / contact_margin
-    const float sp = fmaxf(y, 0.0f) + __logf(1.0f + __expf(-fabsf(y)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(y) * 1.4426950408889634f));
+    const float sp = fmaxf(y, 0.0f) + __logf(1.0f + e);
     const float sc = (0.1f * sp) * rinv;  // contact_force * (sp * contact_margin) / dist
     gx = __fmul_rn(dx, sc);  // never contracted into the caller's accumulation: every kernel variant
     gy = __fmul_rn(dy, sc);  // (thread-per-env, lanes-per-env, fused) produces the same bits
