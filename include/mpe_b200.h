@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MPE_ABI_VERSION 1
+#define MPE_ABI_VERSION 2
 
 enum { MPE_OK = 0, MPE_EINVAL = -1, MPE_ECUDA = -2, MPE_EUNSUPPORTED = -3 };
 enum { MPE_SIMPLE_SPREAD = 0, MPE_SIMPLE_REFERENCE = 1, MPE_SIMPLE_SPEAKER_LISTENER = 2 };
@@ -70,8 +70,9 @@ const char *mpe_last_error(void);
 int mpe_create(const MpeConfig *cfg, MpeEnv **out);
 int mpe_destroy(MpeEnv *env);
 int mpe_query(const MpeEnv *env, MpeDims *out);
-/* env.seed(seed) - main.py:45 */
-int mpe_seed(MpeEnv *env, uint64_t seed);
+/* env.seed(seed) - main.py:45.  Enqueued on `stream`: new Philox key, episode indices restart at 0 with the next
+ * reset, per-episode step counters and running returns are cleared. */
+int mpe_seed(MpeEnv *env, uint64_t seed, void *stream);
 
 /* env.reset() - experiments/run.py:28,60 -> upstream Scenario.reset_world + observation.
  * mask[B] (uint8, may be NULL = all) selects which envs start a new episode; positions ~ U[-1,1)^2,
@@ -107,12 +108,17 @@ int mpe_step(MpeEnv *env, const int32_t *act_u, const int32_t *act_c, const void
 int mpe_step_host(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_host, void *obs_host,
                   void *rew_host, uint8_t *done_host, void *stream);
 
-/* Episode-return bookkeeping (experiments/run.py:23-24,55-57,86-88).  When enabled, every step adds
- * sum_n rew to a per-env accumulator; mpe_reset / auto-reset folds finished episodes into
- * stats = {sum(ret), sum(ret^2), n_episodes, n_steps}. */
+/* Episode-return bookkeeping (experiments/run.py:23-24,55-57,86-88).  When enabled, every mpe_step adds
+ * sum_n rew to a per-env accumulator; mpe_reset folds finished episodes into
+ * stats = {sum(ret), sum(ret^2), n_episodes, n_steps, n_nonfinite_episodes}.  Upstream's collision force divides by
+ * the pair distance without an epsilon, so coincident agents produce NaN (reproduced, not masked): an episode whose
+ * return is not finite is counted in stats[4] and left out of the two sums.
+ * mpe_rollout ALWAYS keeps these counters (its auto-reset needs the per-env episode step) and folds every episode
+ * it finishes, whatever mpe_track_returns says. */
+#define MPE_STATS_LEN 5
 int mpe_track_returns(MpeEnv *env, int32_t enable);
-int mpe_stats_read(MpeEnv *env, double out[4], int32_t clear, void *stream); /* host sync */
-int mpe_stats_ptr(MpeEnv *env, double **dev_ptr); /* device pointer to the 4 doubles (for NCCL) */
+int mpe_stats_read(MpeEnv *env, double out[MPE_STATS_LEN], int32_t clear, void *stream); /* host sync */
+int mpe_stats_ptr(MpeEnv *env, double **dev_ptr); /* device pointer to the MPE_STATS_LEN doubles (for NCCL) */
 
 /* ---- actor: rls/model/ac_network_multi_gumbel.py:24-67 (+ ac_network_model_multi_gumbel.py) ---- */
 typedef struct {
@@ -187,7 +193,9 @@ int64_t replay_next_idx(const MpeReplay *replay);  /* buffer._next_idx    */
 int replay_add(MpeReplay *replay, const float *obs, const int32_t *act_u, const int32_t *act_c, const float *rew,
                const float *obs_next, const float *done, int64_t B, void *stream);
 /* ReplayBuffer.make_index + sample_index: idx [batch] int64 device indices, or NULL to draw them uniformly with
- * replacement (Philox keyed by seed and the number of draws so far).  Outputs (each may be NULL): obs / obs_next
+ * replacement (Philox keyed by seed and the number of draws so far).  Caller-supplied indices follow Python list
+ * indexing of ReplayBuffer._storage: negative values count from the end; values still outside [0, len) are clamped
+ * into the ring (never read out of bounds) - validate host-side where an IndexError is wanted.  Outputs (each may be NULL): obs / obs_next
  * [batch][N][D], act_onehot [batch][N][act0+act1], rew [batch], done [batch], idx_out [batch]. */
 int replay_sample(MpeReplay *replay, int64_t batch, const int64_t *idx, uint64_t seed, float *obs, float *act_onehot,
                   float *rew, float *obs_next, float *done, int64_t *idx_out, void *stream);

@@ -7,11 +7,12 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MPE_B200_LIB', os.path.join(HERE, 'libmpe_b200.so'))  # override: A/B builds
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MPE_OK, MPE_EINVAL, MPE_ECUDA, MPE_EUNSUPPORTED = 0, -1, -2, -3
 SCENARIO_IDS = {'simple_spread': 0, 'simple_reference': 1, 'simple_speaker_listener': 2}
 F32, F64 = 0, 1
+STATS_LEN = 5  # MPE_STATS_LEN
 
 
 class MpeConfig(C.Structure):
@@ -54,7 +55,7 @@ SIGNATURES = {
     'mpe_create': (C.c_int, [C.POINTER(MpeConfig), C.POINTER(P)]),
     'mpe_destroy': (C.c_int, [P]),
     'mpe_query': (C.c_int, [P, C.POINTER(MpeDims)]),
-    'mpe_seed': (C.c_int, [P, C.c_uint64]),
+    'mpe_seed': (C.c_int, [P, C.c_uint64, P]),
     'mpe_reset': (C.c_int, [P, P, P, P]),
     'mpe_set_state': (C.c_int, [P, P, P, P, P, P]),
     'mpe_get_state': (C.c_int, [P, P, P, P, P, P]),

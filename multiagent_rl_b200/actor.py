@@ -188,6 +188,10 @@ class ActingTrainer(FusedActingMixin):
             self.sample_seed = int(sample_seed)
 
     def load_models(self, fname):
-        """rls/agent/multiagent/ddpg_gumbel_fix.py:231-241 (actor only)."""
-        from rls import arglist  # noqa: the reference's config module, present when used as a drop-in
-        self.actor.load_state_dict(torch.load('./Models/' + arglist.appx + str(fname) + '_actor.pt'))
+        """rls/agent/multiagent/ddpg_gumbel_fix.py:231-236 (actor only): the caller passes the full stem -
+        experiments/run.py:117 already prepends ``arglist.appx`` - so the path is './Models/<fname>_actor.pt'."""
+        self.actor.load_state_dict(torch.load('./Models/' + str(fname) + '_actor.pt', map_location=self.device))
+
+    def save_models(self, fname):
+        """rls/agent/multiagent/ddpg_gumbel_fix.py:221-229 (actor only; this stand-in has no target network)."""
+        torch.save(self.actor.state_dict(), './Models/' + str(fname) + '_actor.pt')

@@ -136,7 +136,7 @@ int mpe_create(const MpeConfig *cfg, MpeEnv **out) {
   alloc(reinterpret_cast<void **>(&s.goal), B * sizeof(int32_t), 0xFF);
   alloc(reinterpret_cast<void **>(&s.episode), B * sizeof(uint32_t), 0xFF);  // first reset -> episode 0
   alloc(reinterpret_cast<void **>(&s.tstep), B * sizeof(int32_t), 0);
-  alloc(reinterpret_cast<void **>(&s.stats), 4 * sizeof(double), 0);
+  alloc(reinterpret_cast<void **>(&s.stats), 8 * sizeof(double), 0);  // MPE_STATS_LEN used, padded to 64 B
   if (cfg->scenario == MPE_SIMPLE_REFERENCE) alloc(&s.comm, (size_t)N * dimc * B * rs, 0);
   if (e != cudaSuccess) {
     mpe_destroy(env);
@@ -168,12 +168,19 @@ int mpe_query(const MpeEnv *env, MpeDims *out) {
   return MPE_OK;
 }
 
-int mpe_seed(MpeEnv *env, uint64_t seed) {
+int mpe_seed(MpeEnv *env, uint64_t seed, void *stream) {
   if (env == nullptr) return fail(MPE_EINVAL, "mpe_seed: null env");
   DeviceGuard g(env->device);
-  env->st.seed = seed;
-  // restart the episode counters so that (seed, env id, episode) streams are reproducible
-  CK(cudaMemsetAsync(env->st.episode, 0xFF, (size_t)env->st.B * sizeof(uint32_t), 0));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mpe::EnvStateAny &s = env->st;
+  s.seed = seed;
+  // restart the episode counters so that (seed, env id, episode) streams are reproducible, and drop the
+  // half-finished episodes' bookkeeping (the next reset starts episode 0 of the new seed)
+  CK(cudaMemsetAsync(s.episode, 0xFF, (size_t)s.B * sizeof(uint32_t), st));
+  CK(cudaMemsetAsync(s.tstep, 0, (size_t)s.B * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(s.ep_ret, 0, (size_t)s.B * real_size(s.precision), st));
+  env->synced = false;
+  env->host_tstep = 0;
   return MPE_OK;
 }
 
@@ -223,6 +230,8 @@ int mpe_step(MpeEnv *env, const int32_t *act_u, const int32_t *act_c, const void
 int mpe_step_host(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_host, void *obs_host, void *rew_host,
                   uint8_t *done_host, void *stream) {
   if (env == nullptr || act_u_host == nullptr) return fail(MPE_EINVAL, "mpe_step_host: null env or act_u");
+  if (env->st.scenario == MPE_SIMPLE_REFERENCE && act_c_host == nullptr)
+    return fail(MPE_EINVAL, "mpe_step_host: simple_reference needs act_c");
   DeviceGuard g(env->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const mpe::EnvStateAny &s = env->st;
@@ -237,8 +246,6 @@ int mpe_step_host(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_h
   CK(cudaMemcpyAsync(env->h_act_u, act_u_host, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   if (act_c_host != nullptr)
     CK(cudaMemcpyAsync(env->h_act_c, act_c_host, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  else if (s.scenario == MPE_SIMPLE_REFERENCE)
-    return fail(MPE_EINVAL, "mpe_step_host: simple_reference needs act_c");
   CK(mpe::launch_step(s, env->h_act_u, act_c_host != nullptr ? env->h_act_c : nullptr, nullptr,
                       obs_host != nullptr ? env->h_obs : nullptr, rew_host != nullptr ? env->h_rew : nullptr,
                       done_host != nullptr ? env->h_done : nullptr, nullptr, nullptr, st));
@@ -255,12 +262,12 @@ int mpe_track_returns(MpeEnv *env, int32_t enable) {
   return MPE_OK;
 }
 
-int mpe_stats_read(MpeEnv *env, double out[4], int32_t clear, void *stream) {
+int mpe_stats_read(MpeEnv *env, double out[MPE_STATS_LEN], int32_t clear, void *stream) {
   if (env == nullptr || out == nullptr) return fail(MPE_EINVAL, "mpe_stats_read: null argument");
   DeviceGuard g(env->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CK(cudaMemcpyAsync(out, env->st.stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (clear) CK(cudaMemsetAsync(env->st.stats, 0, 4 * sizeof(double), st));
+  CK(cudaMemcpyAsync(out, env->st.stats, MPE_STATS_LEN * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (clear) CK(cudaMemsetAsync(env->st.stats, 0, MPE_STATS_LEN * sizeof(double), st));
   CK(cudaStreamSynchronize(st));
   return MPE_OK;
 }
@@ -274,6 +281,8 @@ int mpe_stats_ptr(MpeEnv *env, double **dev_ptr) {
 // ------------------------------------------------------------------------------------------------
 // actor
 // ------------------------------------------------------------------------------------------------
+int actor_destroy(MpeActor *a);
+
 int actor_create(const ActorConfig *cfg, MpeActor **out) {
   if (cfg == nullptr || out == nullptr) return fail(MPE_EINVAL, "actor_create: null argument");
   *out = nullptr;
@@ -297,7 +306,7 @@ int actor_create(const ActorConfig *cfg, MpeActor **out) {
     e = cudaMalloc(&a->dev.tc.scratch, mpe::tc_scratch_floats(nsm > 0 ? nsm : 148) * sizeof(float));
   }
   if (e != cudaSuccess) {
-    delete a;
+    actor_destroy(a);  // frees whatever was allocated before the failure
     return fail_cuda(e, "actor_create: cudaMalloc");
   }
   *out = a;
@@ -564,7 +573,7 @@ int replay_sample(MpeReplay *r, int64_t batch, const int64_t *idx, uint64_t seed
     CK(cudaMemcpyAsync(idx_out, idx, (size_t)batch * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   }
   if (obs != nullptr || act_onehot != nullptr || rew != nullptr || obs_next != nullptr || done != nullptr)
-    CK(mpe::launch_replay_gather(r->dev, batch, use, obs, act_onehot, rew, obs_next, done, st));
+    CK(mpe::launch_replay_gather(r->dev, r->size, batch, use, obs, act_onehot, rew, obs_next, done, st));
   if (idx == nullptr) r->draws += 1;
   return MPE_OK;
 }

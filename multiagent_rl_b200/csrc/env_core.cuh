@@ -44,7 +44,7 @@ struct EnvState {
   int32_t *tstep;     // [B]  steps taken in the current episode
   T *ep_ret;          // [B]  running episode return, summed over agents
   T *comm;            // [N][DIMC][B] last message of every agent (simple_reference only, else NULL)
-  double *stats;      // [4]  sum(ret), sum(ret^2), n_episodes, n_steps
+  double *stats;      // [kStatsLen]  sum(ret), sum(ret^2), n_episodes, n_steps, n_nonfinite_episodes
   int64_t B;
   int64_t gid0;       // global id of env 0
   uint64_t seed;
@@ -107,22 +107,28 @@ struct Underflow<double> {
   static constexpr double v = 0.75;
 };
 
-// Fold finished episodes of a warp into stats = {sum ret, sum ret^2, episodes, steps}.
+// Fold finished episodes of a warp into stats = {sum ret, sum ret^2, episodes, steps, non-finite episodes}.
+// Upstream divides by the pair distance without an epsilon, so coincident agents give NaN forces (replicated, not
+// "fixed"); an episode whose return is not finite is COUNTED in stats[4] and kept out of the two sums, so one such
+// episode does not poison the running statistics.  Mean return = stats[0] / (stats[2] - stats[4]).
 __device__ __forceinline__ void fold_stats(double *stats, double ret, double n_ep, double n_steps) {
   if (!__any_sync(0xffffffffu, n_ep != 0.0)) return;  // no episode of this warp ended in this step (the usual case)
-  double a = ret * n_ep, b = ret * ret * n_ep, c = n_ep, d = n_steps;
+  const bool bad = n_ep != 0.0 && !(fabs(ret) <= 1.7976931348623157e308);
+  double a = bad ? 0.0 : ret * n_ep, b = bad ? 0.0 : ret * ret * n_ep, c = n_ep, d = n_steps, e = bad ? 1.0 : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, o);
     b += __shfl_xor_sync(0xffffffffu, b, o);
     c += __shfl_xor_sync(0xffffffffu, c, o);
     d += __shfl_xor_sync(0xffffffffu, d, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
   }
   if ((threadIdx.x & 31) == 0 && c > 0.0) {
     atomicAdd(stats + 0, a);
     atomicAdd(stats + 1, b);
     atomicAdd(stats + 2, c);
     atomicAdd(stats + 3, d);
+    if (e > 0.0) atomicAdd(stats + 4, e);
   }
 }
 

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_replay_make_index(int64_t size, int64_t
 
 // gather `batch` transitions by index
 template <int V>
-__global__ void __launch_bounds__(256) k_replay_gather(ReplayDev r, int64_t batch, const int64_t *__restrict__ idx,
+__global__ void __launch_bounds__(256) k_replay_gather(ReplayDev r, int64_t size, int64_t batch, const int64_t *__restrict__ idx,
                                                        float *__restrict__ obs, float *__restrict__ act_onehot,
                                                        float *__restrict__ rew, float *__restrict__ obs_next,
                                                        float *__restrict__ done) {
@@ -65,7 +65,11 @@ __global__ void __launch_bounds__(256) k_replay_gather(ReplayDev r, int64_t batc
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = i / RV;
     const int c = (int)(i - j * RV);
-    const int64_t slot = idx[j];
+    // list indexing of ReplayBuffer._storage[i] (rls/replay_buffer.py:42): negative indices count from the end;
+    // anything still outside [0, size) is clamped so that a stale index can never read outside the ring
+    int64_t slot = idx[j];
+    if (slot < 0) slot += size;
+    slot = slot < 0 ? 0 : (slot >= size ? size - 1 : slot);
     if (V == 2) {
       if (obs != nullptr) reinterpret_cast<float2 *>(obs + j * R)[c] = reinterpret_cast<const float2 *>(r.obs + slot * R)[c];
       if (obs_next != nullptr)
@@ -112,15 +116,15 @@ cudaError_t launch_replay_make_index(int64_t size, int64_t batch, uint64_t seed,
   return cudaGetLastError();
 }
 
-cudaError_t launch_replay_gather(const ReplayDev &r, int64_t batch, const int64_t *idx, float *obs, float *act_onehot,
+cudaError_t launch_replay_gather(const ReplayDev &r, int64_t size, int64_t batch, const int64_t *idx, float *obs, float *act_onehot,
                                  float *rew, float *obs_next, float *done, cudaStream_t st) {
   if (batch <= 0) return cudaSuccess;
   const int R = r.N * r.D;
   const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(obs_next)) & 7) == 0;
   if (v2)
-    k_replay_gather<2><<<grid_for(batch * (R / 2)), 256, 0, st>>>(r, batch, idx, obs, act_onehot, rew, obs_next, done);
+    k_replay_gather<2><<<grid_for(batch * (R / 2)), 256, 0, st>>>(r, size, batch, idx, obs, act_onehot, rew, obs_next, done);
   else
-    k_replay_gather<1><<<grid_for(batch * R), 256, 0, st>>>(r, batch, idx, obs, act_onehot, rew, obs_next, done);
+    k_replay_gather<1><<<grid_for(batch * R), 256, 0, st>>>(r, size, batch, idx, obs, act_onehot, rew, obs_next, done);
   return cudaGetLastError();
 }
 

@@ -18,7 +18,7 @@ cudaError_t launch_replay_add(const ReplayDev &r, int64_t head, int64_t B, const
                               cudaStream_t st);
 cudaError_t launch_replay_make_index(int64_t size, int64_t batch, uint64_t seed, uint64_t counter, int64_t *idx,
                                      cudaStream_t st);
-cudaError_t launch_replay_gather(const ReplayDev &r, int64_t batch, const int64_t *idx, float *obs, float *act_onehot,
+cudaError_t launch_replay_gather(const ReplayDev &r, int64_t size, int64_t batch, const int64_t *idx, float *obs, float *act_onehot,
                                  float *rew, float *obs_next, float *done, cudaStream_t st);
 
 }  // namespace mpe

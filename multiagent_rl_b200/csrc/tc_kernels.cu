@@ -1512,7 +1512,8 @@ static cudaError_t launch_tc_t(const EnvState<float> &s, const TcDev &w, const A
 }
 
 bool tc_actor_supported(const TcDev &w, int N) {
-  return tc_supported(w) && (N == 2 || N == 3 || ((N == 4 || N == 6 || N == 9 || N == 12) && w.scratch != nullptr));
+  // teams of > 3 agents keep one head of <= 8 entries (launch_actor_forward_tc); wider heads go to the FFMA kernel
+  return tc_supported(w) && (N == 2 || N == 3 || ((N == 4 || N == 6 || N == 9 || N == 12) && w.A <= 8 && w.scratch != nullptr));
 }
 bool tc_rollout_supported(const TcDev &w, int N) { return tc_supported(w) && (N == 2 || N == 3); }
 size_t tc_scratch_floats(int sm_count) {

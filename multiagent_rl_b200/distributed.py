@@ -41,18 +41,20 @@ def init_from_env(backend=None):
 
 
 def reduce_return_stats(local_stats, device=None, group=None):
-    """All-reduce [sum(ret), sum(ret^2), n_episodes, n_steps] (float64) over ranks and derive
-    mean / std of the episode return.  Works on NCCL (cuda tensor) and gloo (cpu tensor)."""
+    """All-reduce [sum(ret), sum(ret^2), n_episodes, n_steps(, n_nonfinite_episodes)] (float64) over ranks and
+    derive mean / std of the episode return over the finite episodes.  Works on NCCL (cuda tensor) and gloo (cpu)."""
     t = torch.as_tensor(np.asarray(local_stats, dtype=np.float64))
     if device is not None:
         t = t.to(device)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     s = t.cpu().numpy()
-    n = s[2]
+    nonfinite = float(s[4]) if len(s) > 4 else 0.0
+    n = s[2] - nonfinite
     mean = s[0] / n if n > 0 else float('nan')
     var = max(s[1] / n - mean * mean, 0.0) if n > 0 else float('nan')
-    return {'sum': s[0], 'sumsq': s[1], 'episodes': n, 'steps': s[3], 'mean_return': mean,
+    return {'sum': s[0], 'sumsq': s[1], 'episodes': s[2], 'steps': s[3], 'nonfinite_episodes': nonfinite,
+            'mean_return': mean,
             'std_return': float(np.sqrt(var)) if n > 0 else float('nan')}
 
 

@@ -60,6 +60,7 @@ class BatchedMultiAgentEnv(object):
         self.precision = precision
         self.dtype = {'fp32': torch.float32, 'fp64': torch.float64}[precision]
         self.benchmark = benchmark
+        self.max_episode_len = int(max_episode_len)  # rls/arglist.py:5; EpisodeHistory.for_env reads it
         self.rng = rng if rng is not None else ('numpy' if not self.batched else 'philox')
         self.env_id_offset = int(env_id_offset)
         cfg = _lib.MpeConfig(scenario=_lib.SCENARIO_IDS[scenario_name], num_agents=0 if n is None else int(n),
@@ -120,7 +121,7 @@ class BatchedMultiAgentEnv(object):
         seed = 1 if seed is None else int(seed)
         np.random.seed(seed)
         self._seed = seed
-        _lib.check(self._lib.mpe_seed(self._h, C.c_uint64(seed & (2 ** 64 - 1))), 'mpe_seed')
+        _lib.check(self._lib.mpe_seed(self._h, C.c_uint64(seed & (2 ** 64 - 1)), self._stream()), 'mpe_seed')
         return [seed]
 
     def render(self, mode='human', close=False):
@@ -210,6 +211,8 @@ class BatchedMultiAgentEnv(object):
             info_n = {'n': [rew_n[i] for i in range(N)]}
         else:
             info_n = {'n': [{} for _ in range(N)]}
+        if self.shared_reward:  # upstream MultiAgentEnv.step: world.collaborative -> every agent gets the sum
+            rew_n = [np.sum(rew_n)] * N
         return obs_n, rew_n, done_n, info_n
 
     # ------------------------------------------------------------------ tensor surface
@@ -279,21 +282,22 @@ class BatchedMultiAgentEnv(object):
         _lib.check(self._lib.mpe_track_returns(self._h, 1 if enable else 0), 'mpe_track_returns')
 
     def stats_tensor(self):
-        """Zero-copy float64[4] CUDA tensor aliasing the shard's statistics (for NCCL reductions without a host
-        sync): [sum(return), sum(return^2), n_episodes, n_steps].  Valid while the env is alive."""
+        """Zero-copy float64[5] CUDA tensor aliasing the shard's statistics (for NCCL reductions without a host
+        sync): [sum(return), sum(return^2), n_episodes, n_steps, n_nonfinite_episodes].  Valid while the env is alive."""
         p = C.c_void_p()
         _lib.check(self._lib.mpe_stats_ptr(self._h, C.byref(p)), 'mpe_stats_ptr')
 
         class _Alias(object):
-            __cuda_array_interface__ = {'shape': (4,), 'typestr': '<f8', 'data': (int(p.value), False), 'version': 2}
+            __cuda_array_interface__ = {'shape': (_lib.STATS_LEN,), 'typestr': '<f8', 'data': (int(p.value), False), 'version': 2}
         with torch.cuda.device(self.device):
             t = torch.as_tensor(_Alias(), device=self.device)
         t._mpe_owner = self  # keep the env (and the device buffer) alive
         return t
 
     def read_stats(self, clear=False):
-        """-> np.array([sum(return), sum(return^2), n_episodes, n_steps]) for this shard (host sync)."""
-        out = (C.c_double * 4)()
+        """-> np.array([sum(return), sum(return^2), n_episodes, n_steps, n_nonfinite_episodes]) for this shard
+        (host sync).  Episodes with a NaN/inf return (coincident agents, like upstream) are counted in [4] only."""
+        out = (C.c_double * _lib.STATS_LEN)()
         _lib.check(self._lib.mpe_stats_read(self._h, out, 1 if clear else 0, self._stream()), 'mpe_stats_read')
         return np.array(list(out), dtype=np.float64)
 

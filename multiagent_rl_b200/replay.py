@@ -7,6 +7,7 @@ appended in env order, as if the reference loop had added them one by one.  Ever
 """
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -22,6 +23,7 @@ class DeviceReplayBuffer(object):
             self.device = torch.device('cuda', torch.cuda.current_device())
         act_dims = [int(act_dims)] if not isinstance(act_dims, (list, tuple)) else [int(a) for a in act_dims]
         self.N, self.D, self.act_dims, self.A = int(num_agents), int(obs_dim), act_dims, sum(act_dims)
+        self.A1 = act_dims[1] if len(act_dims) > 1 else 0
         self._maxsize = int(size)
         self.seed = int(seed)
         cfg = _lib.ReplayConfig(capacity=self._maxsize, num_agents=self.N, obs_dim=self.D, act0=act_dims[0],
@@ -57,7 +59,15 @@ class DeviceReplayBuffer(object):
         actor; reward [B,N] per-agent rewards (summed to the shared reward like run.py:46); done [B] or None."""
         obs, nxt, rew = self._f32(obs_t), self._f32(obs_tp1), self._f32(reward)
         au, ac, dn = self._i32(action), self._i32(act_c), self._f32(done)
+        if obs.dim() != 3 or tuple(obs.shape[1:]) != (self.N, self.D):
+            raise ValueError('obs_t must be [B, %d, %d], got %s' % (self.N, self.D, tuple(obs.shape)))
         B = obs.shape[0]
+        if self.A1 > 0 and ac is None:
+            raise ValueError('act_c is required for a two-head actor')
+        for name, t, want in (('obs_tp1', nxt, B * self.N * self.D), ('action', au, B * self.N),
+                              ('act_c', ac, B * self.N), ('reward', rew, B * self.N), ('done', dn, B)):
+            if t is not None and t.numel() != want:  # the kernels index these raw pointers by B, N, D
+                raise ValueError('%s has %d elements, expected %d' % (name, t.numel(), want))
         _lib.check(self._lib.replay_add(self._h, _lib.ptr(obs), _lib.ptr(au), _lib.ptr(ac), _lib.ptr(rew),
                                         _lib.ptr(nxt), _lib.ptr(dn), B, _lib.current_stream(self.device)), 'replay_add')
 
@@ -86,6 +96,12 @@ class DeviceReplayBuffer(object):
 
     def sample_index(self, idxes):
         """-> (obs [n,N,D], act one-hot [n,N,A], rew_shared [n], obs_next [n,N,D], done [n]) device tensors."""
+        if not (isinstance(idxes, torch.Tensor) and idxes.is_cuda):
+            host = np.asarray(idxes.cpu() if isinstance(idxes, torch.Tensor) else idxes, dtype=np.int64).reshape(-1)
+            n = len(self)
+            if host.size and (host.min() < -n or host.max() >= n):  # list indexing of ReplayBuffer._storage
+                raise IndexError('replay index out of range (len %d)' % n)
+        # device-resident indices cannot be checked without a sync: the gather kernel wraps negatives and clamps
         idx = torch.as_tensor(idxes, dtype=torch.int64, device=self.device).contiguous()
         out, _ = self._gather(idx.numel(), idx)
         return out

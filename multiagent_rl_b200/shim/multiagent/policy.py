@@ -1,0 +1,9 @@
+"""``multiagent.policy``: upstream's Policy base class (test_env/custom_policy.py:5)."""
+
+
+class Policy(object):
+    def __init__(self):
+        pass
+
+    def action(self, obs):
+        raise NotImplementedError()

@@ -75,3 +75,27 @@ def test_rollout_feeds_replay():
     o, a, r, n, d = buf.sample_index(torch.arange(B, 2 * B))  # the transitions of step 1
     assert torch.equal(o, nxt[0]) and torch.equal(n, nxt[1]) and torch.allclose(r, rew[1].sum(1), atol=1e-5)
     assert torch.equal(a.argmax(-1).int(), au[1]) and float(d.abs().max()) == 0.0
+
+
+def test_replay_rejects_mismatched_tensors_and_bad_indices():
+    import multiagent_rl_b200 as m
+    rb = m.DeviceReplayBuffer(64, 3, 10, 5)
+    obs = torch.zeros((8, 3, 10), device='cuda')
+    act = torch.zeros((8, 3), dtype=torch.int32, device='cuda')
+    rew = torch.zeros((8, 3), device='cuda')
+    with pytest.raises(ValueError):
+        rb.add(obs, act[:4], rew, obs)
+    with pytest.raises(ValueError):
+        rb.add(obs, act, rew[:, :2], obs)
+    with pytest.raises(ValueError):
+        rb.add(obs[:, :2], act, rew, obs)
+    rb.add(obs + torch.arange(8, device='cuda').view(8, 1, 1), act, rew, obs)
+    with pytest.raises(IndexError):
+        rb.sample_index([0, 8])
+    with pytest.raises(IndexError):
+        rb.sample_index(np.array([-9]))
+    o = rb.sample_index([-1, 0])[0]   # Python list indexing: -1 is the newest transition
+    assert float(o[0, 0, 0]) == 7.0 and float(o[1, 0, 0]) == 0.0
+    # device-resident indices cannot raise without a sync: out-of-range values are clamped into the ring
+    o = rb.sample_index(torch.tensor([1000, -1000, -2], device='cuda'))[0]
+    assert [float(x) for x in o[:, 0, 0]] == [7.0, 0.0, 6.0]

@@ -139,3 +139,29 @@ def test_episode_history_matches_the_reference_bookkeeping(tmp_path):
         back = pickle.load(fp)
     assert set(back) == {'reward_episodes', 'reward_episodes_by_agents'} and len(back['reward_episodes_by_agents']) == N
     assert len(back['reward_episodes']) == B * E + 1
+
+
+def test_acting_trainer_checkpoint_names_match_the_reference(tmp_path, monkeypatch):
+    """rls/agent/multiagent/ddpg_gumbel_fix.py:221-236: './Models/' + fname + '_actor.pt', where the caller
+    (experiments/run.py:117) has already put arglist.appx into fname - the prefix must not be applied twice."""
+    from multiagent_rl_b200.actor import ActingTrainer
+    monkeypatch.chdir(tmp_path)
+    appx = 'scalability/madr/'  # rls/arglist.py:29
+    os.makedirs(os.path.join('Models', appx))
+    net = ActorNetwork(10, 5)
+    tr = ActingTrainer(net, None, None, 'Discrete', device='cpu')
+    fname = appx + 'simple_spread' + '_fin_' + str(0)
+    tr.save_models(fname)
+    assert os.path.exists('./Models/scalability/madr/simple_spread_fin_0_actor.pt')
+    want = {k: v.clone() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        for p in net.parameters():
+            p.zero_()
+    tr.load_models(fname)
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, want[k])
+
+
+def test_reduce_counts_nonfinite_episodes_separately():
+    out = D.reduce_return_stats([10.0, 60.0, 3.0, 75.0, 1.0])  # 3 episodes, one of them NaN (kept out of the sums)
+    assert out['episodes'] == 3 and out['nonfinite_episodes'] == 1 and out['mean_return'] == 5.0
