@@ -38,7 +38,9 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=2000)
     ap.add_argument('--warmup', type=int, default=50)
-    ap.add_argument('--envs', type=int, default=65536, help='env instances per GPU')
+    ap.add_argument('--envs', type=int, default=None,
+                    help='env instances per GPU (default: 65,536 at --gpus 1 = BASELINE configs[1]; 131,072 at '
+                         '--gpus N > 1, so that 8 GPUs carry configs[4]\'s >= 1M envs)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='budget of the cpu_baseline sample')
     ap.add_argument('--no-extras', action='store_true', help='skip the env-only / 1M-env side measurements')
@@ -197,6 +199,11 @@ class Clocks(object):
         return out
 
 
+def _lib_stats_len():
+    from multiagent_rl_b200 import _lib
+    return _lib.STATS_LEN
+
+
 def physical_gpu_index(local_rank):
     vis = os.environ.get('CUDA_VISIBLE_DEVICES')
     if vis:
@@ -222,7 +229,8 @@ def run_b200(args):
         raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch with torchrun)' % (args.gpus, world))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    B = args.envs
+    numa_cores = D.bind_to_gpu_numa(physical_gpu_index(local))  # before any pinned allocation (first touch)
+    B = args.envs if args.envs else (65536 if world == 1 else 131072)
     off = rank * B
     pk = peaks()
 
@@ -234,7 +242,7 @@ def run_b200(args):
     rew = torch.empty((1, B, N_AGENTS), device=dev)
     act = torch.empty((1, B, N_AGENTS), dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    stats = torch.zeros(_lib_stats_len(), dtype=torch.float64, device=dev)
     stats_dev = env.stats_tensor()  # aliases the device statistics of this shard
     from multiagent_rl_b200 import _lib
     lib = _lib.load()
@@ -249,13 +257,30 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # The path's only collective - the all-reduce of the episode-return statistics, once per episode - runs on a SIDE
+    # stream behind an event, never on the step stream (nothing on the per-step path).
+    side = torch.cuda.Stream(device=dev)
+    reduces = [0]
+
+    def reduce_stats_off_stream():
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            stats.copy_(stats_dev, non_blocking=True)
+            dist.all_reduce(stats)
+        reduces[0] += 1
+
     t = 0
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         fused_step(t)
         t += 1
+        if world > 1 and t % EP_LEN == 0:
+            reduce_stats_off_stream()
     clocks = Clocks(physical_gpu_index(local))
     clocks.start()
+    side.synchronize()
     sync_all()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
@@ -265,51 +290,86 @@ def run_b200(args):
         fused_step(t)
         launches += 1
         t += 1
-        if world > 1 and t % EP_LEN == 0:  # the path's only collective: episode-return statistics (no host sync)
-            stats.copy_(stats_dev)
-            dist.all_reduce(stats)
         ev[k][1].record()
+        if world > 1 and t % EP_LEN == 0:
+            reduce_stats_off_stream()
+    side.synchronize()
     sync_all()
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    ms = sum(per_step)
     ms = D.max_over_ranks(ms, device=dev)
     clk = clocks.stop()
+    stats_now = D.reduce_return_stats(env.read_stats(), device=dev)
     value = world * B * N_AGENTS * args.steps / (ms * 1e-3)
     kernel_s = ms * 1e-3 / args.steps
     tflops = B * FLOPS_PER_ENV_STEP / kernel_s / 1e12
 
-    # ---- e2e: the reference-facing host-buffer calls (get_exploration_action + env.step), pinned memory
-    e2e_steps = max(10, min(args.steps, 50))
-    h_obs = torch.empty((B, N_AGENTS, OBS_DIM), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty((B, N_AGENTS), dtype=torch.float32).pin_memory()
-    h_done = torch.empty((B, N_AGENTS), dtype=torch.uint8).pin_memory()
-    h_act = torch.empty((B, N_AGENTS), dtype=torch.int32).pin_memory()
+    # ---- e2e: the reference-facing host-buffer path (get_exploration_action + env.step with HOST tensors).
+    # Every step uploads every env's observations and actions and downloads its actions, observations, rewards and
+    # dones.  HostRollout keeps `shards` independent shards in different phases on their own streams, so the two PCIe
+    # directions are busy at the same time; the blocking pair (actor_forward_host + mpe_step_host) is timed beside it.
+    rows = B * N_AGENTS
+    e2e_steps = max(25, min(args.steps, 100))
+    del env
+    best = None
+    for shards in (3, 4, 2):
+        hr = m.HostRollout(SCENARIO, B, actor, shards=shards, seed=SEED, env_id_offset=off, device=dev,
+                           max_episode_len=EP_LEN)
+        seen = [0.0]
+
+        def consume(k, tr, seen=seen):  # every step's result is read on the host: a slice of the rewards
+            seen[0] += float(tr.rew_np[:64].sum())
+        for _ in range(5):
+            hr.step(consume)
+        hr.flush(consume)
+        sync_all()
+        w0 = time.perf_counter()
+        for k in range(e2e_steps):
+            hr.step(consume)
+        hr.flush(consume)
+        wall = time.perf_counter() - w0
+        sync_all()
+        if best is None or wall < best[0]:
+            best = (wall, shards)
+        assert np.isfinite(seen[0])
+        del hr
+    e2e_ms = D.max_over_ranks(best[0] * 1e3, device=dev)
+    resets = e2e_steps // EP_LEN
+    e2e = {'value': world * rows * e2e_steps / (e2e_ms * 1e-3), 'unit': 'agent-steps/s',
+           'h2d_bytes_per_step': rows * OBS_DIM * 4,
+           'd2h_bytes_per_step': rows * 4 + rows * OBS_DIM * 4 + rows * 4 + rows + resets * rows * OBS_DIM * 4 // e2e_steps,
+           'steps': e2e_steps, 'shards': best[1], 'depth': 2,
+           'timing': 'host wall clock around K steps incl. delivering every step\'s results to the host callback, max over ranks',
+           'api': 'HostRollout.step: mpe_act_step_host_async per shard on its own stream (H2D observations, actor, env '
+                  'step, one D2H of {actions, observations, rewards, dones}), cudaHostAlloc host buffers, mpe_host_wait '
+                  'before a shard\'s results are read'}
+    # the blocking pair of calls, for comparison (what round 1 reported as e2e)
+    env = m.make_env(SCENARIO, num_envs=B, batched=True, seed=SEED, env_id_offset=off, max_episode_len=EP_LEN)
+    blk = _lib.HostBlock(rows * (OBS_DIM * 4 + 4 + 1 + 4) + 4096)  # cudaHostAlloc staging (not tensor.pin_memory())
+    h_obs = blk.tensor((B, N_AGENTS, OBS_DIM), torch.float32)
+    h_rew = blk.tensor((B, N_AGENTS), torch.float32)
+    h_done = blk.tensor((B, N_AGENTS), torch.uint8)
+    h_act = blk.tensor((B, N_AGENTS), torch.int32)
     h_obs.copy_(env.reset())
     for _ in range(3):
         actor.act_host(h_obs, step=t, env_id_offset=off, act_u=h_act)
         env.step_host(h_act, out=(h_obs, h_rew, h_done))
     sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
-    e0.record()
-    for k in range(e2e_steps):
+    for k in range(25):
         actor.act_host(h_obs, step=t + k, env_id_offset=off, act_u=h_act)  # H2D obs, kernel, D2H actions
         env.step_host(h_act, out=(h_obs, h_rew, h_done))                  # H2D actions, kernel, D2H obs/rew/done
-        if (k + 1) % EP_LEN == 0:
-            h_obs.copy_(env.reset())
-    e1.record()
-    sync_all()
-    e2e_ms = D.max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3), device=dev)
-    rows = B * N_AGENTS
-    e2e = {'value': world * rows * e2e_steps / (e2e_ms * 1e-3), 'unit': 'agent-steps/s',
-           'h2d_bytes_per_step': rows * OBS_DIM * 4 + rows * 4,
-           'd2h_bytes_per_step': rows * 4 + rows * OBS_DIM * 4 + rows * 4 + rows,
-           'steps': e2e_steps, 'api': 'actor_forward_host + mpe_step_host (pinned host buffers)'}
+    blocking_ms = D.max_over_ranks((time.perf_counter() - w0) * 1e3, device=dev)
+    e2e['blocking_calls_value'] = world * rows * 25 / (blocking_ms * 1e-3)
+    torch.cuda.synchronize()
+    del h_obs, h_rew, h_done, h_act
+    blk.free()
+    e2e['pcie_probe'] = pcie_probe(torch, dev, world, D, _lib)
 
     extras = {}
     if not args.no_extras:
         extras = side_measurements(m, actor, dev, pk, off)
 
-    stats_now = D.reduce_return_stats(env.read_stats(), device=dev)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -335,13 +395,50 @@ def run_b200(args):
                      'note': 'algorithmic (fp32-equivalent) FLOPs; every product is issued as 3 fp16 MMAs for fp32-level '
                              'accuracy, so tensor-pipe work is 3x this; the kernel is bound by the MUFU/issue cost of the '
                              'LSTM cell math between the GEMMs (see DESIGN.md 4.3), not by the tensor pipe'},
-        'e2e': e2e, 'gpu_launches': launches, 'clocks': clk,
+        'step_ms_percentiles': {'p50': float(np.percentile(per_step, 50)), 'p99': float(np.percentile(per_step, 99)),
+                                'max': float(np.max(per_step))},
+        'stats_allreduces': {'count': reduces[0], 'where': 'side stream behind an event, once per %d steps; not inside '
+                             'any step\'s event pair' % EP_LEN},
+        'e2e': e2e, 'gpu_launches': launches, 'clocks': clk, 'host_cores_bound': len(numa_cores),
         'episode_stats': {k: stats_now[k] for k in ('episodes', 'mean_return', 'std_return')},
     }
     line.update(extras)
     if world == 1:
         line['cpu_baseline'] = cpu_baseline(args.cpu_seconds)
     print(json.dumps(line), flush=True)
+
+
+def pcie_probe(torch, dev, world, D, _lib):
+    """Plain pinned-memory copies, 8 MiB each way: one direction alone, then both at once on two streams - the
+    ceiling of the host-buffer path on this box (all ranks run it at the same time, like the e2e loop)."""
+    n = 8 << 20
+    blk = _lib.HostBlock(2 * n + 1024)
+    h_in, h_out = blk.tensor((n,), torch.uint8), blk.tensor((n,), torch.uint8)
+    d_in, d_out = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    reps = 40
+
+    def run(up, down):
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return D.max_over_ranks(time.perf_counter() - t0, device=dev)
+    run(True, True)
+    t_up, t_down, t_both = run(True, False), run(False, True), run(True, True)
+    gb = reps * n / 1e9
+    del h_in, h_out
+    blk.free()
+    return {'h2d_gbs': gb / t_up, 'd2h_gbs': gb / t_down, 'duplex_gbs_each_way': gb / t_both,
+            'note': 'per GPU, all ranks copying at once, 8 MiB cudaHostAlloc buffers'}
 
 
 def side_measurements(m, actor, dev, pk, off):

@@ -107,6 +107,35 @@ int mpe_step(MpeEnv *env, const int32_t *act_u, const int32_t *act_c, const void
  * obs/rew/done, then a stream synchronise.  This is what a list-of-numpy caller pays. */
 int mpe_step_host(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_host, void *obs_host,
                   void *rew_host, uint8_t *done_host, void *stream);
+/* The same three stages ENQUEUED on `stream` without the final synchronise, so that a caller that splits its envs
+ * over several handles and streams overlaps one shard's download with another shard's upload (PCIe is full
+ * duplex; the blocking pair above alternates directions).  Host buffers must be pinned and stay untouched until
+ * mpe_host_wait(stream).  mpe_reset_host_async: env.reset() (experiments/run.py:28,60) + D2H of the observations. */
+int mpe_step_host_async(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_host, void *obs_host,
+                        void *rew_host, uint8_t *done_host, void *stream);
+int mpe_reset_host_async(MpeEnv *env, void *obs_host, void *stream);
+/* cudaStreamSynchronize(stream): everything the *_host_async calls enqueued on it has landed in host memory. */
+int mpe_host_wait(void *stream);
+/* One iteration of experiments/run.py:36-44 for a caller whose observations live in host memory:
+ *   get_exploration_action(obs) -> env.step(action)
+ * as H2D obs_host [B][N][D] -> actor forward + sample (Philox keyed by the env's seed, global env ids and `step`) ->
+ * env step on the sampled actions -> ONE D2H of the transition block {act_u, act_c, obs', rew, done} laid out as
+ * mpe_host_block_layout says (offsets in bytes, each 256 B aligned; act_u / act_c int32 [B][N], obs' fp32 [B][N][D],
+ * rew fp32 [B][N], done uint8 [B][N]).  Compared with actor_forward_host_async + mpe_step_host_async the sampled
+ * actions are not bounced through the host before the step reads them and the four downloads are one copy; every
+ * step still uploads the observations and downloads everything the two calls return.  Enqueued on `stream`, no host
+ * synchronisation (mpe_host_wait).  fp32 envs. */
+typedef struct {
+  uint64_t off_act_u, off_act_c, off_obs, off_rew, off_done, bytes;
+} MpeHostBlockLayout;
+int mpe_host_block_layout(const MpeEnv *env, MpeHostBlockLayout *out);
+int mpe_act_step_host_async(MpeEnv *env, MpeActor *actor, const float *obs_host, uint64_t step, void *block_host,
+                            void *stream);
+/* Page-locked staging memory for the *_host entry points, straight from cudaHostAlloc.  (Measured on the B200 pool:
+ * uploads from cudaHostAlloc memory run at 54 GB/s, from torch's pin_memory() blocks at 14 - 18 GB/s - torch 2.11's
+ * caching host allocator hands out memory the copy engine reads three times slower; tools/h2d_probe.py.) */
+int mpe_host_alloc(void **out, uint64_t bytes);
+int mpe_host_free(void *p);
 
 /* Episode-return bookkeeping (experiments/run.py:23-24,55-57,86-88).  When enabled, every mpe_step adds
  * sum_n rew to a per-env accumulator; mpe_reset folds finished episodes into
@@ -164,6 +193,12 @@ int actor_forward(MpeActor *actor, const float *obs, int64_t B, int32_t N, const
 int actor_forward_host(MpeActor *actor, const float *obs_host, int64_t B, int32_t N, uint64_t seed,
                        uint64_t step, int64_t env_id_offset, int32_t *act_u_host, int32_t *act_c_host,
                        float *onehot_host, void *stream);
+/* Same without the final synchronise (ddpg_gumbel_fix.py:93-100 split into enqueue + mpe_host_wait).  `slot`
+ * (0..3) picks one of the handle's independent sets of device mirrors: calls in flight at the same time on
+ * different streams must use different slots. */
+int actor_forward_host_async(MpeActor *actor, const float *obs_host, int64_t B, int32_t N, uint64_t seed,
+                             uint64_t step, int64_t env_id_offset, int32_t *act_u_host, int32_t *act_c_host,
+                             float *onehot_host, int32_t slot, void *stream);
 
 /* The loop body of experiments/run.py:36-65 fused: for t in [0, T): observe -> actor -> sample ->
  * step -> reward -> (episode_step == max_episode_len ? reset), state never leaving the SM between

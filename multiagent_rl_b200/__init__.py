@@ -14,7 +14,8 @@ from .actor import ActingTrainer, FusedActingMixin, FusedActor  # noqa: F401
 from .networks import ActorNetwork  # noqa: F401
 from .replay import DeviceReplayBuffer  # noqa: F401
 from .history import EpisodeHistory  # noqa: F401
+from .hostpipe import HostRollout  # noqa: F401
 from . import distributed  # noqa: F401
 
 __all__ = ['make_env', 'BatchedMultiAgentEnv', 'FusedActor', 'FusedActingMixin', 'ActingTrainer',
-           'ActorNetwork', 'DeviceReplayBuffer', 'EpisodeHistory', 'distributed']
+           'ActorNetwork', 'DeviceReplayBuffer', 'EpisodeHistory', 'HostRollout', 'distributed']

@@ -29,6 +29,10 @@ class MpeDims(C.Structure):
                 ('env_id_offset', C.c_int64)]
 
 
+class MpeHostBlockLayout(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ('off_act_u', 'off_act_c', 'off_obs', 'off_rew', 'off_done', 'bytes')]
+
+
 class ReplayConfig(C.Structure):
     _fields_ = [('capacity', C.c_int64), ('num_agents', C.c_int32), ('obs_dim', C.c_int32), ('act0', C.c_int32),
                 ('act1', C.c_int32), ('device', C.c_int32), ('reserved0', C.c_int32)]
@@ -62,6 +66,13 @@ SIGNATURES = {
     'mpe_observe': (C.c_int, [P, P, P]),
     'mpe_step': (C.c_int, [P, P, P, P, P, P, P, P, P, P]),
     'mpe_step_host': (C.c_int, [P, P, P, P, P, P, P]),
+    'mpe_step_host_async': (C.c_int, [P, P, P, P, P, P, P]),
+    'mpe_reset_host_async': (C.c_int, [P, P, P]),
+    'mpe_host_wait': (C.c_int, [P]),
+    'mpe_host_block_layout': (C.c_int, [P, C.POINTER(MpeHostBlockLayout)]),
+    'mpe_act_step_host_async': (C.c_int, [P, P, P, C.c_uint64, P, P]),
+    'mpe_host_alloc': (C.c_int, [C.POINTER(P), C.c_uint64]),
+    'mpe_host_free': (C.c_int, [P]),
     'mpe_track_returns': (C.c_int, [P, C.c_int32]),
     'mpe_stats_read': (C.c_int, [P, C.POINTER(C.c_double), C.c_int32, P]),
     'mpe_stats_ptr': (C.c_int, [P, C.POINTER(P)]),
@@ -71,6 +82,8 @@ SIGNATURES = {
     'actor_set_impl': (C.c_int, [P, C.c_int32]),
     'actor_forward': (C.c_int, [P, P, C.c_int64, C.c_int32, P, C.c_uint64, C.c_uint64, C.c_int64, P, P, P, P, P, P]),
     'actor_forward_host': (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, P, P, P, P]),
+    'actor_forward_host_async': (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, P, P, P,
+                                           C.c_int32, P]),
     'mpe_rollout': (C.c_int, [P, P, C.c_int32, C.c_uint64, P, P, P, P, P]),
     'replay_create': (C.c_int, [C.POINTER(ReplayConfig), C.POINTER(P)]),
     'replay_destroy': (C.c_int, [P]),
@@ -123,3 +136,58 @@ def ptr(t):
 def current_stream(device):
     import torch
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class HostBlock(object):
+    """Page-locked host memory from cudaHostAlloc (``mpe_host_alloc``), carved into torch tensors.
+
+    Use this - not ``tensor.pin_memory()`` - for the buffers handed to the ``*_host`` entry points: on the B200 pool
+    the copy engine uploads from torch's pinned blocks at 14 - 18 GB/s and from cudaHostAlloc memory at 54 GB/s
+    (tools/h2d_probe.py).  The tensors are views: they are valid until ``free()`` / garbage collection of the block."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(load().mpe_host_alloc(C.byref(p), self.nbytes), 'mpe_host_alloc')
+        self.ptr = p.value
+        self._used = 0
+        self._views = []
+
+    def tensor(self, shape, dtype, offset=None):
+        """A slice of the block as a tensor of the given shape / torch dtype: at byte ``offset``, or (default) the
+        next unused 256 B-aligned position."""
+        import torch
+        n = 1
+        for d in shape:
+            n *= int(d)
+        size = n * torch.empty((), dtype=dtype).element_size()
+        off = (self._used + 255) // 256 * 256 if offset is None else int(offset)
+        if off + size > self.nbytes:
+            raise ValueError('HostBlock of %d bytes is full' % self.nbytes)
+        if offset is None:
+            self._used = off + size
+        if size == 0:
+            return torch.empty(shape, dtype=dtype)
+        buf = (C.c_uint8 * size).from_address(self.ptr + off)
+        t = torch.frombuffer(buf, dtype=torch.uint8).view(dtype).view(*shape)
+        self._views.append(buf)
+        return t
+
+    @staticmethod
+    def size_for(specs):
+        """Bytes needed for a list of (shape, torch dtype), each 256 B aligned."""
+        import torch
+        total = 0
+        for shape, dtype in specs:
+            n = 1
+            for d in shape:
+                n *= int(d)
+            total = (total + 255) // 256 * 256 + n * torch.empty((), dtype=dtype).element_size()
+        return total + 256
+
+    def free(self):
+        if getattr(self, 'ptr', None):
+            load().mpe_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    __del__ = free

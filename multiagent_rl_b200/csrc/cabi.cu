@@ -34,13 +34,15 @@ int fail_cuda(cudaError_t e, const char *where) {
 
 struct DeviceGuard {
   int prev = -1;
-  bool ok = true;
+  bool ok = true, switched = false;
   explicit DeviceGuard(int dev) {
     if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
-    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    if (prev != dev) {
+      if (cudaSetDevice(dev) != cudaSuccess) ok = false; else switched = true;
+    }
   }
   ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
+    if (switched) cudaSetDevice(prev);  // the common case - already on the handle's device - costs one cudaGetDevice
   }
 };
 
@@ -58,16 +60,25 @@ struct MpeEnv {
   // scratch of the multi-kernel rollout (teams of > 3 agents): current observations and sampled actions
   float *r_obs = nullptr;
   int32_t *r_act = nullptr;
+  // mpe_act_step_host_async: device mirror of the caller's observations and of its transition block
+  float *hb_obs_in = nullptr;
+  unsigned char *hb_block = nullptr;
   bool synced = false;      // all envs are at the same episode step (true after an unmasked reset)
   int32_t host_tstep = 0;   // that common episode step
+};
+
+constexpr int kHostSlots = 4;  // independent sets of device mirrors: that many *_host_async calls may be in flight
+
+struct ActorMirror {
+  float *obs = nullptr, *onehot = nullptr;  // device mirrors for actor_forward_host[_async]
+  int32_t *act_u = nullptr, *act_c = nullptr;
+  int64_t cap = 0;  // capacity in rows (B*N)
 };
 
 struct MpeActor {
   mpe::ActorDev dev;
   int device = 0;
-  float *h_obs = nullptr, *h_onehot = nullptr;  // device mirrors for actor_forward_host
-  int32_t *h_act_u = nullptr, *h_act_c = nullptr;
-  int64_t h_cap = 0;  // capacity in rows (B*N)
+  ActorMirror mirror[kHostSlots];
 };
 
 struct MpeReplay {
@@ -152,7 +163,8 @@ int mpe_destroy(MpeEnv *env) {
   cudaDeviceSynchronize();
   mpe::EnvStateAny &s = env->st;
   void *ptrs[] = {s.pv, s.lm, s.ep_ret, s.comm, s.goal, s.episode, s.tstep, s.stats,
-                  env->h_act_u, env->h_act_c, env->h_obs, env->h_rew, env->h_done, env->r_obs, env->r_act};
+                  env->h_act_u, env->h_act_c, env->h_obs, env->h_rew, env->h_done, env->r_obs, env->r_act,
+                  env->hb_obs_in, env->hb_block};
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
   delete env;
@@ -227,13 +239,12 @@ int mpe_step(MpeEnv *env, const int32_t *act_u, const int32_t *act_c, const void
   return MPE_OK;
 }
 
-int mpe_step_host(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_host, void *obs_host, void *rew_host,
-                  uint8_t *done_host, void *stream) {
-  if (env == nullptr || act_u_host == nullptr) return fail(MPE_EINVAL, "mpe_step_host: null env or act_u");
+static int mpe_step_host_impl(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_host, void *obs_host,
+                              void *rew_host, uint8_t *done_host, cudaStream_t st, bool sync, const char *who) {
+  if (env == nullptr || act_u_host == nullptr) return fail(MPE_EINVAL, std::string(who) + ": null env or act_u");
   if (env->st.scenario == MPE_SIMPLE_REFERENCE && act_c_host == nullptr)
-    return fail(MPE_EINVAL, "mpe_step_host: simple_reference needs act_c");
+    return fail(MPE_EINVAL, std::string(who) + ": simple_reference needs act_c");
   DeviceGuard g(env->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const mpe::EnvStateAny &s = env->st;
   const size_t rows = (size_t)s.B * s.N, rs = real_size(s.precision);
   if (env->h_act_u == nullptr) {
@@ -249,10 +260,43 @@ int mpe_step_host(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_h
   CK(mpe::launch_step(s, env->h_act_u, act_c_host != nullptr ? env->h_act_c : nullptr, nullptr,
                       obs_host != nullptr ? env->h_obs : nullptr, rew_host != nullptr ? env->h_rew : nullptr,
                       done_host != nullptr ? env->h_done : nullptr, nullptr, nullptr, st));
+  if (env->st.track) env->host_tstep += 1; else env->synced = false;
   if (obs_host != nullptr) CK(cudaMemcpyAsync(obs_host, env->h_obs, rows * s.D * rs, cudaMemcpyDeviceToHost, st));
   if (rew_host != nullptr) CK(cudaMemcpyAsync(rew_host, env->h_rew, rows * rs, cudaMemcpyDeviceToHost, st));
   if (done_host != nullptr) CK(cudaMemcpyAsync(done_host, env->h_done, rows, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (sync) CK(cudaStreamSynchronize(st));
+  return MPE_OK;
+}
+
+int mpe_step_host(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_host, void *obs_host, void *rew_host,
+                  uint8_t *done_host, void *stream) {
+  return mpe_step_host_impl(env, act_u_host, act_c_host, obs_host, rew_host, done_host, static_cast<cudaStream_t>(stream),
+                            true, "mpe_step_host");
+}
+
+int mpe_step_host_async(MpeEnv *env, const int32_t *act_u_host, const int32_t *act_c_host, void *obs_host,
+                        void *rew_host, uint8_t *done_host, void *stream) {
+  return mpe_step_host_impl(env, act_u_host, act_c_host, obs_host, rew_host, done_host, static_cast<cudaStream_t>(stream),
+                            false, "mpe_step_host_async");
+}
+
+int mpe_reset_host_async(MpeEnv *env, void *obs_host, void *stream) {
+  if (env == nullptr || obs_host == nullptr) return fail(MPE_EINVAL, "mpe_reset_host_async: null argument");
+  DeviceGuard g(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const mpe::EnvStateAny &s = env->st;
+  const size_t rows = (size_t)s.B * s.N, rs = real_size(s.precision);
+  if (env->h_obs == nullptr) {
+    CK(cudaMalloc(&env->h_act_u, rows * sizeof(int32_t)));
+    CK(cudaMalloc(&env->h_act_c, rows * sizeof(int32_t)));
+    CK(cudaMalloc(&env->h_obs, rows * s.D * rs));
+    CK(cudaMalloc(&env->h_rew, rows * rs));
+    CK(cudaMalloc(&env->h_done, rows));
+  }
+  CK(mpe::launch_reset(s, nullptr, env->h_obs, 0, st));
+  env->synced = true;
+  env->host_tstep = 0;
+  CK(cudaMemcpyAsync(obs_host, env->h_obs, rows * s.D * rs, cudaMemcpyDeviceToHost, st));
   return MPE_OK;
 }
 
@@ -317,9 +361,14 @@ int actor_destroy(MpeActor *a) {
   if (a == nullptr) return MPE_OK;
   DeviceGuard g(a->device);
   cudaDeviceSynchronize();
-  void *ptrs[] = {a->dev.blob, a->dev.tc.blob, a->dev.tc.scratch, a->h_obs, a->h_onehot, a->h_act_u, a->h_act_c};
+  void *ptrs[] = {a->dev.blob, a->dev.tc.blob, a->dev.tc.scratch};
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
+  for (ActorMirror &m : a->mirror) {
+    void *mp[] = {m.obs, m.onehot, m.act_u, m.act_c};
+    for (void *p : mp)
+      if (p != nullptr) cudaFree(p);
+  }
   delete a;
   return MPE_OK;
 }
@@ -388,42 +437,132 @@ int actor_forward(MpeActor *a, const float *obs, int64_t B, int32_t N, const flo
   return MPE_OK;
 }
 
-int actor_forward_host(MpeActor *a, const float *obs_host, int64_t B, int32_t N, uint64_t seed, uint64_t step,
-                       int64_t env_id_offset, int32_t *act_u_host, int32_t *act_c_host, float *onehot_host,
-                       void *stream) {
-  if (a == nullptr || obs_host == nullptr) return fail(MPE_EINVAL, "actor_forward_host: null argument");
+// H2D obs -> forward + sample -> D2H actions, all enqueued on `st`; `sync` waits for the stream at the end.
+static int actor_forward_host_impl(MpeActor *a, const float *obs_host, int64_t B, int32_t N, uint64_t seed, uint64_t step,
+                                   int64_t env_id_offset, int32_t *act_u_host, int32_t *act_c_host, float *onehot_host,
+                                   int32_t slot, cudaStream_t st, bool sync, const char *who) {
+  if (a == nullptr || obs_host == nullptr) return fail(MPE_EINVAL, std::string(who) + ": null argument");
+  if (slot < 0 || slot >= kHostSlots) return fail(MPE_EINVAL, std::string(who) + ": slot out of range");
   if (B <= 0) return MPE_OK;
-  if (!mpe::actor_supported(N)) return fail(MPE_EUNSUPPORTED, "actor_forward_host: unsupported agent count");
+  if (!mpe::actor_supported(N)) return fail(MPE_EUNSUPPORTED, std::string(who) + ": unsupported agent count");
   DeviceGuard g(a->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = B * N;
   const int A = a->dev.A0 + a->dev.A1;
-  if (rows > a->h_cap) {
-    void *old[] = {a->h_obs, a->h_onehot, a->h_act_u, a->h_act_c};
+  ActorMirror &m = a->mirror[slot];
+  if (rows > m.cap) {
+    // growing a mirror frees the old one: wait for whatever the stream still has in flight on it
+    if (m.cap > 0) CK(cudaStreamSynchronize(st));
+    void *old[] = {m.obs, m.onehot, m.act_u, m.act_c};
     for (void *p : old)
       if (p != nullptr) cudaFree(p);
-    a->h_obs = a->h_onehot = nullptr; a->h_act_u = a->h_act_c = nullptr; a->h_cap = 0;
-    CK(cudaMalloc(&a->h_obs, (size_t)rows * a->dev.D * sizeof(float)));
-    CK(cudaMalloc(&a->h_onehot, (size_t)rows * A * sizeof(float)));
-    CK(cudaMalloc(&a->h_act_u, (size_t)rows * sizeof(int32_t)));
-    CK(cudaMalloc(&a->h_act_c, (size_t)rows * sizeof(int32_t)));
-    a->h_cap = rows;
+    m = ActorMirror();
+    CK(cudaMalloc(&m.obs, (size_t)rows * a->dev.D * sizeof(float)));
+    CK(cudaMalloc(&m.onehot, (size_t)rows * A * sizeof(float)));
+    CK(cudaMalloc(&m.act_u, (size_t)rows * sizeof(int32_t)));
+    CK(cudaMalloc(&m.act_c, (size_t)rows * sizeof(int32_t)));
+    m.cap = rows;
   }
-  CK(cudaMemcpyAsync(a->h_obs, obs_host, (size_t)rows * a->dev.D * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m.obs, obs_host, (size_t)rows * a->dev.D * sizeof(float), cudaMemcpyHostToDevice, st));
   mpe::ActorIO io;
-  io.obs = a->h_obs; io.act_u = a->h_act_u; io.act_c = a->dev.A1 > 0 ? a->h_act_c : nullptr;
-  io.onehot = onehot_host != nullptr ? a->h_onehot : nullptr;
+  io.obs = m.obs; io.act_u = m.act_u; io.act_c = a->dev.A1 > 0 ? m.act_c : nullptr;
+  io.onehot = onehot_host != nullptr ? m.onehot : nullptr;
   io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
   if (use_tc(a, N, false))
     CK(mpe::launch_actor_forward_tc(a->dev.tc, io, st));
   else
     CK(mpe::launch_actor_forward(a->dev, io, st));
-  if (act_u_host != nullptr) CK(cudaMemcpyAsync(act_u_host, a->h_act_u, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (act_u_host != nullptr) CK(cudaMemcpyAsync(act_u_host, m.act_u, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (act_c_host != nullptr && a->dev.A1 > 0)
-    CK(cudaMemcpyAsync(act_c_host, a->h_act_c, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(act_c_host, m.act_c, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (onehot_host != nullptr)
-    CK(cudaMemcpyAsync(onehot_host, a->h_onehot, (size_t)rows * A * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpyAsync(onehot_host, m.onehot, (size_t)rows * A * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (sync) CK(cudaStreamSynchronize(st));
+  return MPE_OK;
+}
+
+int actor_forward_host(MpeActor *a, const float *obs_host, int64_t B, int32_t N, uint64_t seed, uint64_t step,
+                       int64_t env_id_offset, int32_t *act_u_host, int32_t *act_c_host, float *onehot_host,
+                       void *stream) {
+  return actor_forward_host_impl(a, obs_host, B, N, seed, step, env_id_offset, act_u_host, act_c_host, onehot_host, 0,
+                                 static_cast<cudaStream_t>(stream), true, "actor_forward_host");
+}
+
+int actor_forward_host_async(MpeActor *a, const float *obs_host, int64_t B, int32_t N, uint64_t seed, uint64_t step,
+                             int64_t env_id_offset, int32_t *act_u_host, int32_t *act_c_host, float *onehot_host,
+                             int32_t slot, void *stream) {
+  return actor_forward_host_impl(a, obs_host, B, N, seed, step, env_id_offset, act_u_host, act_c_host, onehot_host, slot,
+                                 static_cast<cudaStream_t>(stream), false, "actor_forward_host_async");
+}
+
+static MpeHostBlockLayout block_layout(const mpe::EnvStateAny &s) {
+  const uint64_t rows = (uint64_t)s.B * s.N, rs = real_size(s.precision);
+  auto up = [](uint64_t x) { return (x + 255) / 256 * 256; };
+  MpeHostBlockLayout l;
+  l.off_act_u = 0;
+  l.off_act_c = up(l.off_act_u + rows * 4);
+  l.off_obs = up(l.off_act_c + rows * 4);
+  l.off_rew = up(l.off_obs + rows * s.D * rs);
+  l.off_done = up(l.off_rew + rows * rs);
+  l.bytes = up(l.off_done + rows);
+  return l;
+}
+
+int mpe_host_block_layout(const MpeEnv *env, MpeHostBlockLayout *out) {
+  if (env == nullptr || out == nullptr) return fail(MPE_EINVAL, "mpe_host_block_layout: null argument");
+  *out = block_layout(env->st);
+  return MPE_OK;
+}
+
+int mpe_act_step_host_async(MpeEnv *env, MpeActor *actor, const float *obs_host, uint64_t step, void *block_host,
+                            void *stream) {
+  if (env == nullptr || actor == nullptr || obs_host == nullptr || block_host == nullptr)
+    return fail(MPE_EINVAL, "mpe_act_step_host_async: null argument");
+  mpe::EnvStateAny &s = env->st;
+  if (s.precision != MPE_F32) return fail(MPE_EUNSUPPORTED, "mpe_act_step_host_async: fp32 envs only");
+  if (env->device != actor->device) return fail(MPE_EINVAL, "mpe_act_step_host_async: env and actor on different devices");
+  if (actor->dev.D != s.D || actor->dev.A0 != 5 || actor->dev.A1 != s.act_c)
+    return fail(MPE_EINVAL, "mpe_act_step_host_async: actor does not match the env's observation / action space");
+  if (!mpe::actor_supported(s.N)) return fail(MPE_EUNSUPPORTED, "mpe_act_step_host_async: unsupported agent count");
+  DeviceGuard g(env->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const MpeHostBlockLayout l = block_layout(s);
+  const size_t rows = (size_t)s.B * s.N;
+  if (env->hb_block == nullptr) {
+    CK(cudaMalloc(&env->hb_obs_in, rows * s.D * sizeof(float)));
+    CK(cudaMalloc(&env->hb_block, l.bytes));
+    CK(cudaMemsetAsync(env->hb_block, 0, l.bytes, st));
+  }
+  unsigned char *blk = env->hb_block;
+  CK(cudaMemcpyAsync(env->hb_obs_in, obs_host, rows * s.D * sizeof(float), cudaMemcpyHostToDevice, st));
+  mpe::ActorIO io;
+  io.obs = env->hb_obs_in;
+  io.act_u = reinterpret_cast<int32_t *>(blk + l.off_act_u);
+  io.act_c = actor->dev.A1 > 0 ? reinterpret_cast<int32_t *>(blk + l.off_act_c) : nullptr;
+  io.B = s.B; io.N = s.N; io.seed = s.seed; io.step = step; io.gid0 = s.gid0;
+  if (use_tc(actor, s.N, false))
+    CK(mpe::launch_actor_forward_tc(actor->dev.tc, io, st));
+  else
+    CK(mpe::launch_actor_forward(actor->dev, io, st));
+  CK(mpe::launch_step(s, io.act_u, io.act_c, nullptr, blk + l.off_obs, blk + l.off_rew, blk + l.off_done, nullptr, nullptr, st));
+  if (s.track) env->host_tstep += 1; else env->synced = false;
+  CK(cudaMemcpyAsync(block_host, blk, l.bytes, cudaMemcpyDeviceToHost, st));
+  return MPE_OK;
+}
+
+int mpe_host_alloc(void **out, uint64_t bytes) {
+  if (out == nullptr || bytes == 0) return fail(MPE_EINVAL, "mpe_host_alloc: bad argument");
+  *out = nullptr;
+  CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+  return MPE_OK;
+}
+
+int mpe_host_free(void *p) {
+  if (p != nullptr) CK(cudaFreeHost(p));
+  return MPE_OK;
+}
+
+int mpe_host_wait(void *stream) {
+  CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return MPE_OK;
 }
 

@@ -340,17 +340,26 @@ inline EnvState<T> typed(const EnvStateAny &a) {
     }                                                                               \
   } while (0)
 
-template <typename T, typename K>
-inline cudaError_t set_smem(K kernel, int bytes) {
-  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  return cudaSuccess;
+// kernels that stage more than the default 48 KB opt in once per (kernel, device): the attribute is sticky.  The
+// kernel is a template ARGUMENT so that every kernel gets its own "done" flags.
+template <auto Kernel>
+inline cudaError_t set_smem_once(int bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (done[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[dev] = true;
+  return e;
 }
 
 #define MPE_GRP_RESET(NN, GG, DO_RESET)                                                                            \
   {                                                                                                                \
     using GL = GroupLayout<T, NN, GG>;                                                                             \
     constexpr int sm = GL::kBlockBytes;                                                                            \
-    cudaError_t err = set_smem<T>(k_reset_grp<T, NN, GG>, sm);                                                     \
+    cudaError_t err = set_smem_once<k_reset_grp<T, NN, GG>>(sm);                                                     \
     if (err != cudaSuccess) return err;                                                                            \
     const int64_t per_block = (int64_t)GL::EPW * (kStepThreads / 32);                                              \
     k_reset_grp<T, NN, GG><<<(unsigned)((a.B + per_block - 1) / per_block), kStepThreads, sm, st>>>(               \
@@ -370,7 +379,7 @@ cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs,
 #define CALL(SC, NN)                                                                          \
   {                                                                                           \
     constexpr int sm = StageLayout<T, SC, NN>::kBlockBytes;                                   \
-    cudaError_t err = set_smem<T>(k_reset<T, SC, NN>, sm);                                    \
+    cudaError_t err = set_smem_once<k_reset<T, SC, NN>>(sm);                                    \
     if (err != cudaSuccess) return err;                                                       \
     k_reset<T, SC, NN><<<grid, kStepThreads, sm, st>>>(typed<T>(a), mask, static_cast<T *>(obs), auto_len); \
   }
@@ -393,7 +402,7 @@ cudaError_t launch_observe_t(const EnvStateAny &a, void *obs, cudaStream_t st) {
 #define CALL(SC, NN)                                                                    \
   {                                                                                     \
     constexpr int sm = StageLayout<T, SC, NN>::kBlockBytes;                             \
-    cudaError_t err = set_smem<T>(k_observe<T, SC, NN>, sm);                            \
+    cudaError_t err = set_smem_once<k_observe<T, SC, NN>>(sm);                            \
     if (err != cudaSuccess) return err;                                                 \
     k_observe<T, SC, NN><<<grid, kStepThreads, sm, st>>>(typed<T>(a), static_cast<T *>(obs)); \
   }
@@ -411,7 +420,7 @@ cudaError_t launch_step_t(const EnvStateAny &a, const int32_t *act_u, const int3
   {                                                                                                                \
     using GL = GroupLayout<T, NN, GG>;                                                                             \
     constexpr int sm = GL::kBlockBytes;                                                                            \
-    cudaError_t err = set_smem<T>(k_step_grp<T, NN, GG>, sm);                                                      \
+    cudaError_t err = set_smem_once<k_step_grp<T, NN, GG>>(sm);                                                      \
     if (err != cudaSuccess) return err;                                                                            \
     const int64_t per_block = (int64_t)GL::EPW * (kStepThreads / 32);                                              \
     k_step_grp<T, NN, GG><<<(unsigned)((a.B + per_block - 1) / per_block), kStepThreads, sm, st>>>(                \
@@ -427,7 +436,7 @@ cudaError_t launch_step_t(const EnvStateAny &a, const int32_t *act_u, const int3
 #define CALL(SC, NN)                                                                                         \
   {                                                                                                          \
     constexpr int sm = StageLayout<T, SC, NN>::kBlockBytes;                                                  \
-    cudaError_t err = set_smem<T>(k_step<T, SC, NN>, sm);                                                    \
+    cudaError_t err = set_smem_once<k_step<T, SC, NN>>(sm);                                                    \
     if (err != cudaSuccess) return err;                                                                      \
     k_step<T, SC, NN><<<grid, kStepThreads, sm, st>>>(typed<T>(a), act_u, act_c, static_cast<const T *>(comm_vec), \
                                                       static_cast<T *>(obs), static_cast<T *>(rew), done, info_i, \

@@ -1469,25 +1469,48 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
-static int sm_count_tc() {
-  int dev = 0, n = 0;
+// Per-launch host work is kept to the launch itself (the fused step is a ~60 us kernel): the device ordinal is one
+// cheap runtime call, everything derived from it is cached per device.
+static int current_device() {
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  return n > 0 ? n : 148;
+  return (dev >= 0 && dev < 64) ? dev : 0;
+}
+static int sm_count_tc(int dev) {
+  static int cached[64] = {0};
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is sticky per function and device: raise it only when a launch needs more
+template <typename K>
+static cudaError_t ensure_smem(K kernel, size_t bytes, size_t (&have)[64], int dev) {
+  if (have[dev] >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) have[dev] = bytes;
+  return e;
+}
+static int tc_debug_flag() {
+  static const int dbg = getenv("MPE_TC_TIMELINE") != nullptr ? 1 : 0;
+  return dbg;
 }
 
 template <int SC, int N, bool FUSED, int APAD>
 static cudaError_t launch_tc2_t(const EnvState<float> &s, const TcDev &w, const ActorIO &io, const RolloutIO &ro,
                                 int max_episode_len, int64_t nenvs, cudaStream_t st) {
+  static size_t have[64] = {0};
+  const int dev = current_device();
   const size_t smem = tc2_smem_bytes(w.bytes, N, w.Kx, APAD);
-  cudaError_t e = cudaFuncSetAttribute(k_tc2<SC, N, FUSED, APAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_smem(k_tc2<SC, N, FUSED, APAD>, smem, have, dev);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (nenvs + kRows - 1) / kRows;
-  const int nsm = sm_count_tc();
+  const int nsm = sm_count_tc(dev);
   const int64_t pairs = (ntiles + 1) / 2;
   const int grid = (int)(pairs < nsm ? pairs : nsm);
-  k_tc2<SC, N, FUSED, APAD><<<grid, tc2_threads(N), smem, st>>>(s, w, io, ro, max_episode_len, ntiles,
-                                                           getenv("MPE_TC_TIMELINE") != nullptr ? 1 : 0);
+  k_tc2<SC, N, FUSED, APAD><<<grid, tc2_threads(N), smem, st>>>(s, w, io, ro, max_episode_len, ntiles, tc_debug_flag());
   return cudaGetLastError();
 }
 
@@ -1499,15 +1522,16 @@ static cudaError_t launch_tc_t(const EnvState<float> &s, const TcDev &w, const A
     if (!v1 && tc2_smem_bytes(w.bytes, N, w.Kx, APAD) <= 227 * 1024)
       return launch_tc2_t<SC, N, FUSED, APAD>(s, w, io, ro, max_episode_len, nenvs, st);
   }
+  static size_t have[64] = {0};
+  const int dev = current_device();
   const size_t smem = tc_smem_bytes(w.bytes, N, w.Kx);
-  cudaError_t e = cudaFuncSetAttribute(k_tc<SC, N, FUSED, APAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_smem(k_tc<SC, N, FUSED, APAD>, smem, have, dev);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (nenvs + kRows - 1) / kRows;
-  const int nsm = sm_count_tc();
+  const int nsm = sm_count_tc(dev);
   const int64_t pairs = (ntiles + 1) / 2;  // every CTA runs two tile pipelines
   const int grid = (int)(pairs < nsm ? pairs : nsm);
-  static const int dbg = getenv("MPE_TC_TIMELINE") != nullptr;
-  k_tc<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles, dbg);
+  k_tc<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles, tc_debug_flag());
   return cudaGetLastError();
 }
 

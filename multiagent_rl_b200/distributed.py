@@ -40,6 +40,26 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores NVML reports as local to the GPU, BEFORE any pinned host memory is
+    allocated: first-touch then places the staging buffers on the GPU's own NUMA node, so that with one process per
+    GPU the ranks' host<->device copies do not all cross one socket's memory controller.  Returns the core list (empty
+    when NVML or the affinity call is unavailable - the caller carries on unbound)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cores = [64 * w + b for w, bits in enumerate(mask) for b in range(64) if (int(bits) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 - NVML missing / containers without the affinity syscall
+        return []
+
+
 def reduce_return_stats(local_stats, device=None, group=None):
     """All-reduce [sum(ret), sum(ret^2), n_episodes, n_steps(, n_nonfinite_episodes)] (float64) over ranks and
     derive mean / std of the episode return over the finite episodes.  Works on NCCL (cuda tensor) and gloo (cpu)."""

@@ -4,11 +4,13 @@ GPU box with the repo snapshot like the built ``.so``).
 TEST INFRASTRUCTURE (see oracle/__init__.py).  The reference is pure Python, so "compiling the reference" means
 byte-compiling its sources *where they lie* under /root/reference into sourceless ``.pyc`` files:
 
-    python -m oracle.build_ref            # writes oracle/_ref/<package>/<module>.pyc
+    python -m oracle.build_ref            # writes oracle/_ref/<package>/<module>.refpyc
 
 No reference source text enters the repo; the outputs are CPython bytecode for the interpreter of this image
-(the GPU box runs the same image).  ``oracle/_ref`` on ``sys.path`` then serves ``import experiments.run``,
-``import experiments.scenarios``, ``import rls...`` - the UNMODIFIED reference - to
+(the GPU box runs the same image).  The files carry the extension ``.refpyc`` because the gpurun snapshot drops
+``*.pyc``; ``add_to_path()`` installs a meta-path finder that loads them with the stock SourcelessFileLoader, which
+then serves ``import experiments.run``, ``import experiments.scenarios``, ``import rls...`` - the UNMODIFIED
+reference - to
 
   * tests/test_reference_exec.py (CPU): the reference's ``make_env`` + ``local_obs_*``
     (experiments/scenarios.py:6-63,124-192) executed on tests/_stubs/multiagent and compared with the oracle;
@@ -20,6 +22,9 @@ No reference source text enters the repo; the outputs are CPython bytecode for t
 The third-party ``multiagent`` package the reference imports (experiments/scenarios.py:2-3) is NOT part of the
 reference tree and is not produced here; see tests/_stubs/multiagent/__init__.py.
 """
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import os
 import py_compile
 import sys
@@ -27,6 +32,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get('MPE_REFERENCE_ROOT', '/root/reference')
 OUT = os.path.join(HERE, '_ref')
+EXT = '.refpyc'
 
 MODULES = [
     'experiments/scenarios.py',
@@ -46,7 +52,7 @@ MODULES = [
 
 def available():
     """True when the compiled reference is importable from oracle/_ref."""
-    return all(os.path.exists(os.path.join(OUT, m + 'c')) for m in MODULES)
+    return all(os.path.exists(os.path.join(OUT, m[:-3] + EXT)) for m in MODULES)
 
 
 def build(verbose=True):
@@ -55,7 +61,7 @@ def build(verbose=True):
         return False
     for rel in MODULES:
         src = os.path.join(REF, rel)
-        dst = os.path.join(OUT, rel + 'c')
+        dst = os.path.join(OUT, rel[:-3] + EXT)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # dfile: the path shown in tracebacks; file:line citations in this repo are relative to the reference root
         py_compile.compile(src, cfile=dst, dfile='reference/' + rel, doraise=True,
@@ -67,12 +73,27 @@ def build(verbose=True):
     return True
 
 
+class _RefFinder(importlib.abc.MetaPathFinder):
+    """Serves the packages compiled into oracle/_ref (``experiments``, ``rls``) and nothing else."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        rel = os.path.join(OUT, *fullname.split('.'))
+        if os.path.isfile(rel + EXT):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, rel + EXT)
+            return importlib.util.spec_from_file_location(fullname, rel + EXT, loader=loader)
+        if os.path.isdir(rel):  # the reference has no __init__.py files: namespace packages
+            spec = importlib.machinery.ModuleSpec(fullname, None, is_package=True)
+            spec.submodule_search_locations = [rel]
+            return spec
+        return None
+
+
 def add_to_path():
-    """Put the compiled reference (and nothing else of the reference) on sys.path; raises if it was never built."""
+    """Make the compiled reference (and nothing else of the reference) importable; raises if it was never built."""
     if not available():
         raise RuntimeError('oracle/_ref is empty: run `python -m oracle.build_ref` where /root/reference exists')
-    if OUT not in sys.path:
-        sys.path.insert(0, OUT)
+    if not any(isinstance(f, _RefFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefFinder())
     return OUT
 
 

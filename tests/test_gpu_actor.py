@@ -184,8 +184,8 @@ def test_fused_rollout_equals_stepwise_path(scenario, n, B, impl):
 def test_fused_rollout_vs_float64_oracle_directly(scenario, n, B):
     """The fused kernel's env phase against the float64 oracle, not via the stepwise kernels: a full 25-step episode
     of ``rollout(record=True)`` at the bench size (65,536 envs) is replayed by oracle/mpe_vec.py from the same initial
-    state with the RECORDED actions.  fp32 tolerances of tests/test_gpu_env.py: observations 5e-5 worst case and 1e-5
-    at p99.99 per env, rewards 2e-4 (a reward may be off by whole units only where a collision flag sits on its
+    state with the RECORDED actions.  fp32 tolerances of tests/test_gpu_env.py: positions 5e-5 worst case and 1e-5
+    at p99.99 per env, velocities 5e-4, rewards 2e-4 (a reward may be off by whole units only where a collision flag sits on its
     threshold: |dist - 0.30| within the band that env's position error explains)."""
     import multiagent_rl_b200 as m
     T, seed = 25, 4242
@@ -202,12 +202,14 @@ def test_fused_rollout_vs_float64_oracle_directly(scenario, n, B):
     assert np.abs(obs0.cpu().numpy() - v.observe()).max() <= 1e-6
     obs, rew, act_u, act_c = env.rollout(actor, T, step0=0, record=True)
     obs, rew, act_u = obs.cpu().numpy().astype(np.float64), rew.cpu().numpy().astype(np.float64), act_u.cpu().numpy()
-    act_c = act_c.cpu().numpy() if act_c is not None else None
+    # the speaker's message is the first dim_c entries of its width-5 one-hot action (oracle/mpe_ref.py, ambiguity 3)
+    act_c = act_c.cpu().numpy() if act_c is not None else (act_u if scenario == 'simple_speaker_listener' else None)
     worst = np.zeros(B)
     for t in range(T):
         o, r, _ = v.step(act_u[t], act_c[t] if act_c is not None else None)
-        err = np.abs(obs[t] - o).max(axis=(1, 2))
+        err = np.abs(obs[t] - o)[:, :, 2:].max(axis=(1, 2))     # positions and relative landmark positions
         worst = np.maximum(worst, err)
+        assert np.abs(obs[t] - o)[:, :, :2].max() <= 5e-4          # velocities (= position differences / dt)
         dr = np.abs(rew[t] - r)
         if scenario == 'simple_spread':
             band = 2.0 * np.sqrt(2.0) * err + 1e-6
@@ -217,7 +219,15 @@ def test_fused_rollout_vs_float64_oracle_directly(scenario, n, B):
             assert near.mean() < 1e-3
         else:
             assert dr.max() <= 2e-4, (t, dr.max())
-    assert worst.max() <= 5e-5 and np.quantile(worst, 0.9999) <= 1e-5, (worst.max(), np.quantile(worst, 0.9999))
+    # Stiff contacts (contact_margin 1e-3, contact_force 100) multiply a position difference by up to
+    # 100 / 1e-3 * dt^2 = 1e3 per step while two agents overlap, so an fp32 rounding difference of 3e-8 can grow for
+    # as long as a contact lasts; crowded teams (6 - 12 agents in the same arena) spend more steps in contact.
+    # N <= 3: 5e-5 worst case, 1e-5 at p99.99.  Larger teams: 5e-4 worst case, 2e-5 at p99, 2e-6 median.
+    if spec.N <= 3:
+        assert worst.max() <= 5e-5 and np.quantile(worst, 0.9999) <= 1e-5, (worst.max(), np.quantile(worst, 0.9999))
+    else:
+        assert worst.max() <= 5e-4 and np.quantile(worst, 0.99) <= 2e-5 and np.median(worst) <= 2e-6, \
+            (worst.max(), np.quantile(worst, 0.99), np.median(worst))
     assert len(np.unique(act_u)) == 5
 
 
@@ -354,3 +364,50 @@ def test_fused_rollout_equals_stepwise_path_tiny_batches(scenario, n, A):
             assert torch.equal(obs, rec[0][t]) and torch.equal(rew, rec[1][t]), (B, t)
             if (t + 1) % 4 == 0:
                 obs = env2.reset()
+
+
+@pytest.mark.parametrize('scenario,shards,B', [('simple_spread', 3, 5001), ('simple_spread', 1, 700),
+                                               ('simple_reference', 2, 2050), ('simple_spread', 4, 3)])
+def test_host_rollout_shards_match_the_blocking_calls(scenario, shards, B):
+    """HostRollout (non-blocking actor_forward_host_async + mpe_step_host_async per shard and stream) gives, for every
+    shard count, exactly the transitions of the device-tensor calls on one env handle: same Philox keys (global env
+    id, step), same kernels.  Both ends of each transition are on the host: obs_prev -> (act, rew) -> obs."""
+    import multiagent_rl_b200 as m
+    L, seed = 4, 31
+    n = None
+    A = [5, 10] if scenario == 'simple_reference' else 5
+    D = 21 if scenario == 'simple_reference' else 10
+    actor = m.FusedActor(actor_ref.init_state_dict(D, A, 2), seed=seed)
+    hr = m.HostRollout(scenario, B, actor, shards=shards, n=n, seed=seed, max_episode_len=L, track_returns=True)
+    env = m.make_env(scenario, n=n, num_envs=B, batched=True, seed=seed, max_episode_len=L)
+    env.track_returns(True)
+    seen = []
+    cb = lambda k, tr: seen.append((tr.step, k, float(tr.rew_np.sum()), float(tr.obs_prev.sum()), float(tr.obs.sum())))  # noqa: E731
+    want = []
+    obs = None
+    for t in range(10):
+        hr.step(cb)
+        hr.wait()
+        if t % L == 0:
+            obs = env.reset()
+        out = actor.forward(obs, step=t)
+        assert np.array_equal(hr.obs_prev.numpy(), obs.cpu().numpy()), t
+        assert np.array_equal(hr.act_u.numpy(), out['act_u'].cpu().numpy()), t
+        if hr.two_heads:
+            assert np.array_equal(hr.act_c.numpy(), out['act_c'].cpu().numpy()), t
+        prev = obs
+        obs, rew, done, _ = env.step(out['act_u'], out['act_c'])
+        assert np.array_equal(hr.obs.numpy(), obs.cpu().numpy()) and np.array_equal(hr.rew.numpy(), rew.cpu().numpy()), t
+        assert int(hr.done.sum()) == 0
+        for k, sh in enumerate(hr.shards):
+            sl = slice(sh.offset, sh.offset + sh.num_envs)
+            want.append((t, k, float(rew[sl].cpu().numpy().sum()), float(prev[sl].cpu().sum()), float(obs[sl].cpu().sum())))
+    hr.flush(cb)
+    # the callbacks (delivered `depth` steps late, the rest by flush) saw every shard-step once, in step order, with
+    # both ends of the transition intact
+    assert [x[:2] for x in seen] == [x[:2] for x in want]
+    assert np.allclose(np.array(seen), np.array(want), rtol=1e-5, atol=1e-3)
+    env.reset()
+    hr.reset()
+    hr.step()
+    assert np.allclose(hr.read_stats(), env.read_stats(), rtol=1e-9)
