@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(kActorThreads, 1) k_actor_forward(ActorDev w, 
   }
 }
 
+#ifdef MPE_AB_KERNELS  // the fp32 FFMA fused rollout: superseded by k_tc2, A/B builds only
 // ------------------------------------------------------------------------------------------------
 // fused rollout: T x (observe -> actor -> sample -> World.step -> reward -> auto-reset)
 // ------------------------------------------------------------------------------------------------
@@ -520,10 +521,12 @@ __global__ void __launch_bounds__(kActorThreads, 1)
   }
 }
 
+#endif  // MPE_AB_KERNELS
+
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
-bool actor_supported(int N) { return N == 2 || N == 3 || N == 4 || N == 6 || N == 9 || N == 12; }
+bool actor_supported(int N) { return N >= 1 && N <= 12; }  // any team size make_env(n=...) is asked for, up to 12
 bool rollout_supported(int scenario, int N) { return env_supported(scenario, N); }
 
 static int sm_count() {
@@ -538,8 +541,15 @@ static int sm_count() {
 template <int N, int TB, int PAD>
 static cudaError_t launch_actor_t(const ActorDev &w, const ActorIO &io, cudaStream_t st) {
   const size_t smem = ActorSmem<N, TB, PAD>::bytes(w.blob_floats, w.D);
-  cudaError_t e = cudaFuncSetAttribute(k_actor_forward<N, TB, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static size_t have[64] = {0};  // sticky per (kernel, device): raise the opt-in only when a launch needs more
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (have[dev] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_actor_forward<N, TB, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    have[dev] = smem;
+  }
   const int64_t ntiles = (io.B + TB - 1) / TB;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   k_actor_forward<N, TB, PAD><<<grid, kActorThreads, smem, st>>>(w, io, ntiles);
@@ -548,16 +558,23 @@ static cudaError_t launch_actor_t(const ActorDev &w, const ActorIO &io, cudaStre
 
 cudaError_t launch_actor_forward(const ActorDev &w, const ActorIO &io, cudaStream_t st) {
   switch (io.N) {
+    case 1: return launch_actor_t<1, 64, 4>(w, io, st);
     case 2: return launch_actor_t<2, 64, 4>(w, io, st);
     case 3: return launch_actor_t<3, 64, 4>(w, io, st);
     case 4: return launch_actor_t<4, 32, 4>(w, io, st);
+    case 5: return launch_actor_t<5, 32, 4>(w, io, st);
     case 6: return launch_actor_t<6, 32, 0>(w, io, st);
+    case 7: return launch_actor_t<7, 16, 0>(w, io, st);
+    case 8: return launch_actor_t<8, 16, 0>(w, io, st);
     case 9: return launch_actor_t<9, 16, 0>(w, io, st);
+    case 10: return launch_actor_t<10, 16, 0>(w, io, st);
+    case 11: return launch_actor_t<11, 16, 0>(w, io, st);
     case 12: return launch_actor_t<12, 16, 0>(w, io, st);
     default: return cudaErrorInvalidValue;
   }
 }
 
+#ifdef MPE_AB_KERNELS
 template <int SC, int N, int TB, int PAD>
 static cudaError_t launch_rollout_t(const EnvStateAny &a, const ActorDev &w, const RolloutIO &ro, cudaStream_t st) {
   const size_t smem = ActorSmem<N, TB, PAD>::bytes(w.blob_floats, w.D);
@@ -588,5 +605,7 @@ cudaError_t launch_rollout(const EnvStateAny &a, const ActorDev &w, const Rollou
     default: return cudaErrorInvalidValue;
   }
 }
+
+#endif  // MPE_AB_KERNELS
 
 }  // namespace mpe

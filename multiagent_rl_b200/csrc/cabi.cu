@@ -429,7 +429,7 @@ int actor_forward(MpeActor *a, const float *obs, int64_t B, int32_t N, const flo
   io.act_u = act_u; io.act_c = act_c; io.onehot = onehot;
   io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
   if (a->dev.impl == mpe::kImplTc && !use_tc(a, N, next_state != nullptr))
-    return fail(MPE_EUNSUPPORTED, "actor_forward: tensor-core path supports 2/3/4/6/9/12 agents, obs_dim <= 32, <= 8 head entries for > 3 agents, no model head");
+    return fail(MPE_EUNSUPPORTED, "actor_forward: the tensor-core path covers 2/3/4/6/9/12 agents, obs_dim <= 32, <= 8 head entries for > 3 agents, no model head");
   if (use_tc(a, N, next_state != nullptr))
     CK(mpe::launch_actor_forward_tc(a->dev.tc, io, static_cast<cudaStream_t>(stream)));
   else
@@ -582,19 +582,29 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
   mpe::RolloutIO io;
   io.T = T; io.step0 = step0; io.obs_next = obs_next; io.rew = rew; io.act_u = act_u; io.act_c = act_c;
   if (actor->dev.impl != mpe::kImplSimt && mpe::tc_rollout_supported(actor->dev.tc, env->st.N)) {
-    CK(mpe::launch_rollout_tc(env->st, actor->dev.tc, io, st));
+    CK(mpe::launch_rollout_tc(env->st, actor->dev.tc, io, st));  // one kernel for all T steps (teams of <= 3)
     env->synced = false;
-  } else if (actor->dev.impl != mpe::kImplSimt && env->st.scenario == MPE_SIMPLE_SPREAD &&
-             mpe::tc_actor_supported(actor->dev.tc, env->st.N)) {
-    // Teams of > 3 agents: the same loop as two kernels per step - tensor-core actor (k_tc, actor mode) and the
-    // lanes-per-env step kernel - plus a reset kernel on the steps where an episode can end.
+    return MPE_OK;
+  }
+#ifdef MPE_AB_KERNELS
+  if (actor->dev.impl == mpe::kImplSimt) {  // A/B builds: the fp32 FFMA fused kernel
+    CK(mpe::launch_rollout(env->st, actor->dev, io, st));
+    env->synced = false;
+    return MPE_OK;
+  }
+#endif
+  {
+    // Every other combination (teams of > 3 agents, the fp32 FFMA actor): the same loop as kernels per step - actor
+    // (tensor cores where the shape is covered, else FFMA), the env step kernel, and a reset kernel on the steps
+    // where an episode can end.  Same Philox keys, same arithmetic: bit-identical to the stepwise calls.
     mpe::EnvStateAny s = env->st;
     s.track = 1;
     const int64_t rows = s.B * s.N;
     if (env->r_obs == nullptr) {
       CK(cudaMalloc(&env->r_obs, (size_t)rows * s.D * sizeof(float)));
-      CK(cudaMalloc(&env->r_act, (size_t)rows * sizeof(int32_t)));
+      CK(cudaMalloc(&env->r_act, (size_t)rows * 2 * sizeof(int32_t)));
     }
+    const bool tc = use_tc(actor, s.N, false);
     CK(mpe::launch_observe(s, env->r_obs, st));
     const float *cur = env->r_obs;
     const int L = s.max_episode_len;
@@ -602,9 +612,13 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
       mpe::ActorIO aio;
       aio.obs = cur; aio.B = s.B; aio.N = s.N; aio.seed = s.seed; aio.step = step0 + (uint64_t)t; aio.gid0 = s.gid0;
       aio.act_u = act_u != nullptr ? act_u + (int64_t)t * rows : env->r_act;
-      CK(mpe::launch_actor_forward_tc(actor->dev.tc, aio, st));
+      if (s.act_c > 0) aio.act_c = act_c != nullptr ? act_c + (int64_t)t * rows : env->r_act + rows;
+      if (tc)
+        CK(mpe::launch_actor_forward_tc(actor->dev.tc, aio, st));
+      else
+        CK(mpe::launch_actor_forward(actor->dev, aio, st));
       float *o = obs_next != nullptr ? obs_next + (int64_t)t * rows * s.D : env->r_obs;
-      CK(mpe::launch_step(s, aio.act_u, nullptr, nullptr, o, rew != nullptr ? rew + (int64_t)t * rows : nullptr, nullptr,
+      CK(mpe::launch_step(s, aio.act_u, aio.act_c, nullptr, o, rew != nullptr ? rew + (int64_t)t * rows : nullptr, nullptr,
                           nullptr, nullptr, st));
       cur = o;
       env->host_tstep += 1;
@@ -615,9 +629,6 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
         if (env->synced) env->host_tstep = 0;
       }
     }
-  } else {
-    CK(mpe::launch_rollout(env->st, actor->dev, io, st));
-    env->synced = false;
   }
   return MPE_OK;
 }
@@ -722,7 +733,7 @@ int replay_sample(MpeReplay *r, int64_t batch, const int64_t *idx, uint64_t seed
 // precision dispatch for the env launchers declared in env_launch.h
 namespace mpe {
 bool env_supported(int scenario, int N) {
-  if (scenario == 0) return N == 2 || N == 3 || N == 4 || N == 6 || N == 9 || N == 12;
+  if (scenario == 0) return N >= 1 && N <= 12;  // simple_spread: make_world(num_agents=n), experiments/scenarios.py:170
   return (scenario == 1 || scenario == 2) && N == 2;
 }
 cudaError_t launch_reset(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st) {

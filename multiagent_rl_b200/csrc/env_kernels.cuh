@@ -319,16 +319,22 @@ inline EnvState<T> typed(const EnvStateAny &a) {
   return s;
 }
 
+// Team size -> kernel family.  Up to 5 agents: one thread per env (every entity in registers).  6 and more: G lanes
+// per env (env_group.cuh), each owning N / G agents and landmarks; G is the divisor of N that keeps a lane at <= 3
+// agents with the most envs per warp (primes get one agent per lane).
+__host__ __device__ constexpr int group_lanes(int N) {
+  return N <= 5 ? 0 : N == 6 ? 2 : N == 7 ? 7 : N == 8 ? 4 : N == 9 ? 3 : N == 10 ? 5 : N == 11 ? 11 : N == 12 ? 4 : -1;
+}
+
 #define MPE_DISPATCH(a, CALL)                                                       \
   do {                                                                              \
     if ((a).scenario == kSpread) {                                                  \
       switch ((a).N) {                                                              \
-        case 3: CALL(kSpread, 3); break;                                            \
-        case 6: CALL(kSpread, 6); break;                                            \
-        case 9: CALL(kSpread, 9); break;                                            \
-        case 12: CALL(kSpread, 12); break;                                          \
+        case 1: CALL(kSpread, 1); break;                                            \
         case 2: CALL(kSpread, 2); break;                                            \
+        case 3: CALL(kSpread, 3); break;                                            \
         case 4: CALL(kSpread, 4); break;                                            \
+        case 5: CALL(kSpread, 5); break;                                            \
         default: return cudaErrorInvalidValue;                                      \
       }                                                                             \
     } else if ((a).scenario == kReference) {                                        \
@@ -338,6 +344,21 @@ inline EnvState<T> typed(const EnvStateAny &a) {
     } else {                                                                        \
       return cudaErrorInvalidValue;                                                 \
     }                                                                               \
+  } while (0)
+
+// G-lanes-per-env families: GRP(N, G) for every team size of 6..12
+#define MPE_DISPATCH_GRP(a, GRP) \
+  do {                           \
+    switch ((a).N) {             \
+      case 6: GRP(6, 2)          \
+      case 7: GRP(7, 7)          \
+      case 8: GRP(8, 4)          \
+      case 9: GRP(9, 3)          \
+      case 10: GRP(10, 5)        \
+      case 11: GRP(11, 11)       \
+      case 12: GRP(12, 4)        \
+      default: return cudaErrorInvalidValue; \
+    }                            \
   } while (0)
 
 // kernels that stage more than the default 48 KB opt in once per (kernel, device): the attribute is sticky.  The
@@ -370,10 +391,10 @@ inline cudaError_t set_smem_once(int bytes) {
 template <typename T>
 cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
-  if (a.scenario == kSpread && (a.N == 6 || a.N == 9 || a.N == 12)) {  // G lanes per env (env_group.cuh)
-    if (a.N == 6) MPE_GRP_RESET(6, 2, 1)
-    if (a.N == 9) MPE_GRP_RESET(9, 3, 1)
-    MPE_GRP_RESET(12, 4, 1)
+  if (a.scenario == kSpread && group_lanes(a.N) > 0) {  // G lanes per env (env_group.cuh)
+#define GRP(NN, GG) MPE_GRP_RESET(NN, GG, 1)
+    MPE_DISPATCH_GRP(a, GRP);
+#undef GRP
   }
   const unsigned grid = (unsigned)((a.B + kStepThreads - 1) / kStepThreads);
 #define CALL(SC, NN)                                                                          \
@@ -391,12 +412,12 @@ cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs,
 template <typename T>
 cudaError_t launch_observe_t(const EnvStateAny &a, void *obs, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
-  if (a.scenario == kSpread && (a.N == 6 || a.N == 9 || a.N == 12)) {
+  if (a.scenario == kSpread && group_lanes(a.N) > 0) {
     const uint8_t *mask = nullptr;
     const int auto_len = 0;
-    if (a.N == 6) MPE_GRP_RESET(6, 2, 0)
-    if (a.N == 9) MPE_GRP_RESET(9, 3, 0)
-    MPE_GRP_RESET(12, 4, 0)
+#define GRP(NN, GG) MPE_GRP_RESET(NN, GG, 0)
+    MPE_DISPATCH_GRP(a, GRP);
+#undef GRP
   }
   const unsigned grid = (unsigned)((a.B + kStepThreads - 1) / kStepThreads);
 #define CALL(SC, NN)                                                                    \
@@ -415,7 +436,7 @@ template <typename T>
 cudaError_t launch_step_t(const EnvStateAny &a, const int32_t *act_u, const int32_t *act_c, const void *comm_vec,
                           void *obs, void *rew, uint8_t *done, int32_t *info_i, void *info_f, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
-  if (a.scenario == kSpread && (a.N == 6 || a.N == 9 || a.N == 12)) {  // G lanes per env (env_group.cuh)
+  if (a.scenario == kSpread && group_lanes(a.N) > 0) {  // G lanes per env (env_group.cuh)
 #define GRP(NN, GG)                                                                                                \
   {                                                                                                                \
     using GL = GroupLayout<T, NN, GG>;                                                                             \
@@ -427,9 +448,7 @@ cudaError_t launch_step_t(const EnvStateAny &a, const int32_t *act_u, const int3
         typed<T>(a), act_u, static_cast<T *>(obs), static_cast<T *>(rew), done, info_i, static_cast<T *>(info_f)); \
     return cudaGetLastError();                                                                                     \
   }
-    if (a.N == 6) GRP(6, 2)
-    if (a.N == 9) GRP(9, 3)
-    GRP(12, 4)
+    MPE_DISPATCH_GRP(a, GRP);
 #undef GRP
   }
   const unsigned grid = (unsigned)((a.B + kStepThreads - 1) / kStepThreads);

@@ -275,6 +275,7 @@ __device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float 
   if (store_h) store_chunk_split(h_chunk, h_chunk + 8192, row, hv);
 }
 
+#ifdef MPE_AB_KERNELS  // the superseded two-pipeline kernel: A/B builds only (python -m multiagent_rl_b200.build --variant ab MPE_AB_KERNELS)
 // ------------------------------------------------------------------------------------------------
 // the kernel: two independent tile pipelines per CTA (one per warpgroup), sharing the weight image
 //   warps 0-3 / 4-7 : warpgroup g = 0 / 1, thread r of the group owns env row r of the group's tile
@@ -722,6 +723,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   __syncthreads();
   if (warp == 8) tmem_free(tmem_base, 512);
 }
+
+#endif  // MPE_AB_KERNELS
 
 // ------------------------------------------------------------------------------------------------
 // k_tc2 (teams of <= 3 agents): the same two tiles per CTA, but BOTH warpgroups work on EVERY cell - warpgroup h
@@ -1517,22 +1520,24 @@ static cudaError_t launch_tc2_t(const EnvState<float> &s, const TcDev &w, const 
 template <int SC, int N, bool FUSED, int APAD>
 static cudaError_t launch_tc_t(const EnvState<float> &s, const TcDev &w, const ActorIO &io, const RolloutIO &ro,
                                int max_episode_len, int64_t nenvs, cudaStream_t st) {
-  if constexpr (N <= 3 || !FUSED) {
-    static const bool v1 = getenv("MPE_TC_V1") != nullptr;  // A/B switch: the two-independent-pipelines kernel
-    if (!v1 && tc2_smem_bytes(w.bytes, N, w.Kx, APAD) <= 227 * 1024)
-      return launch_tc2_t<SC, N, FUSED, APAD>(s, w, io, ro, max_episode_len, nenvs, st);
+#ifdef MPE_AB_KERNELS
+  static const bool v1 = getenv("MPE_TC_V1") != nullptr;  // A/B switch: the two-independent-pipelines kernel
+  if (v1) {
+    static size_t have[64] = {0};
+    const int dev = current_device();
+    const size_t smem = tc_smem_bytes(w.bytes, N, w.Kx);
+    cudaError_t e = ensure_smem(k_tc<SC, N, FUSED, APAD>, smem, have, dev);
+    if (e != cudaSuccess) return e;
+    const int64_t ntiles = (nenvs + kRows - 1) / kRows;
+    const int nsm = sm_count_tc(dev);
+    const int64_t pairs = (ntiles + 1) / 2;  // every CTA runs two tile pipelines
+    const int grid = (int)(pairs < nsm ? pairs : nsm);
+    k_tc<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles, tc_debug_flag());
+    return cudaGetLastError();
   }
-  static size_t have[64] = {0};
-  const int dev = current_device();
-  const size_t smem = tc_smem_bytes(w.bytes, N, w.Kx);
-  cudaError_t e = ensure_smem(k_tc<SC, N, FUSED, APAD>, smem, have, dev);
-  if (e != cudaSuccess) return e;
-  const int64_t ntiles = (nenvs + kRows - 1) / kRows;
-  const int nsm = sm_count_tc(dev);
-  const int64_t pairs = (ntiles + 1) / 2;  // every CTA runs two tile pipelines
-  const int grid = (int)(pairs < nsm ? pairs : nsm);
-  k_tc<SC, N, FUSED, APAD><<<grid, kTcThreads, smem, st>>>(s, w, io, ro, max_episode_len, ntiles, tc_debug_flag());
-  return cudaGetLastError();
+#endif
+  if (tc2_smem_bytes(w.bytes, N, w.Kx, APAD) > 227 * 1024) return cudaErrorInvalidValue;  // tc_*_supported rule these out
+  return launch_tc2_t<SC, N, FUSED, APAD>(s, w, io, ro, max_episode_len, nenvs, st);
 }
 
 bool tc_actor_supported(const TcDev &w, int N) {
@@ -1543,7 +1548,11 @@ bool tc_rollout_supported(const TcDev &w, int N) { return tc_supported(w) && (N 
 size_t tc_scratch_floats(int sm_count) {
   // the largest of: k_tc's forward shares; k_tc2's per-cell shares for the instantiated large teams (N <= 12, one head
   // of <= 8 entries) and for the two-head small teams (N <= 3, 16 entries)
+#ifdef MPE_AB_KERNELS
   const size_t v1 = (size_t)sm_count * 2 * 12 * 16 * kRows;
+#else
+  const size_t v1 = 0;
+#endif
   const size_t v2 = (size_t)sm_count * tc2_scratch_f2_per_cta(12, 8) * 2, v3 = (size_t)sm_count * tc2_scratch_f2_per_cta(3, 16) * 2;
   return v1 > v2 ? (v1 > v3 ? v1 : v3) : (v2 > v3 ? v2 : v3);
 }

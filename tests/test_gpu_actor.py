@@ -411,3 +411,29 @@ def test_host_rollout_shards_match_the_blocking_calls(scenario, shards, B):
     hr.reset()
     hr.step()
     assert np.allclose(hr.read_stats(), env.read_stats(), rtol=1e-9)
+
+
+@pytest.mark.parametrize('n', [1, 5, 7, 8, 10, 11])
+def test_actor_and_rollout_for_every_team_size(n):
+    """Team sizes without a tensor-core instantiation run the fp32 FFMA actor; their rollout is actor + step (+ reset)
+    kernels per step.  Logits vs the float64 restatement, and the rollout equals the step-by-step calls bit for bit."""
+    import multiagent_rl_b200 as m
+    D, B, L = 4 + 2 * n, 777, 4
+    sd = actor_ref.init_state_dict(D, 5, n)
+    obs = np.random.RandomState(n).uniform(-2, 2, (B, n, D)).astype(np.float32)
+    actor = m.FusedActor(sd, seed=9)
+    out = actor.forward(torch.from_numpy(obs), want_logits=True, step=3)
+    want = actor_ref.forward(sd, obs)['logits'][0]
+    assert np.abs(out['logits'].cpu().numpy() - want).max() <= LOGIT_ATOL
+    env = m.make_env('simple_spread', n=n, num_envs=B, batched=True, seed=9, max_episode_len=L)
+    env2 = m.make_env('simple_spread', n=n, num_envs=B, batched=True, seed=9, max_episode_len=L)
+    env.reset()
+    o = env2.reset()
+    rec = env.rollout(actor, 9, step0=0, record=True)
+    for t in range(9):
+        a = actor.forward(o, step=t)
+        assert torch.equal(a['act_u'], rec[2][t]), t
+        o, rew, _, _ = env2.step(a['act_u'])
+        assert torch.equal(o, rec[0][t]) and torch.equal(rew, rec[1][t]), t
+        if (t + 1) % L == 0:
+            o = env2.reset()

@@ -431,3 +431,39 @@ def test_episode_history_for_env():
         _, rew, _, _ = env.step(torch.zeros((64, 3), dtype=torch.int32, device='cuda'))
         h.add_step(rew)
     assert len(h.finished) == 1 and len(h.history()['reward_episodes']) == 65
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+@pytest.mark.parametrize('n', [1, 2, 4, 5, 7, 8, 10, 11])
+def test_every_team_size_make_env_accepts(n, precision):
+    """experiments/scenarios.py:169-170 passes any ``n`` to make_world(num_agents=n): every team size from 1 to 12 has a
+    kernel (one thread per env up to 5 agents, G lanes per env above), checked against the float64 oracle over an
+    episode from Philox resets with crowded starts; batch sizes that do not fill the last warp."""
+    B, T = 1000 + n, 25
+    env = _mk('simple_spread', n, B, precision, seed=100 + n)
+    obs0 = env.reset()
+    pos, vel, lm, _ = env.get_state()
+    pos = pos * 0.35  # crowd the agents into a third of the arena so that contacts happen
+    env.set_state(pos, vel, lm)
+    spec = mpe_vec.Spec('simple_spread', n)
+    v = mpe_vec.VecEnv(spec, B)
+    v.set_state(_np(pos), _np(vel), _np(lm))
+    assert obs0.shape == (B, n, 4 + 2 * n)
+    _check(_np(env.observe()), v.observe(), precision, 'obs0', 1e-6)
+    rng = np.random.RandomState(n)
+    worst, contacts = np.zeros(B), 0
+    for t in range(T):
+        act = rng.randint(0, 5, (B, n)).astype(np.int32)
+        obs, rew, done, info = env.step(act, info=True)
+        o, r, (coll, occ) = v.step(act)
+        contacts += int((coll > 1).sum())
+        ii = info['info_i'].cpu().numpy()
+        if precision == 'fp64':
+            assert np.abs(_np(obs) - o).max() <= F64_ATOL and np.abs(_np(rew) - r).max() <= F64_ATOL, t
+            assert np.array_equal(ii[:, :n], coll) and np.array_equal(ii[:, n], occ)
+        else:
+            worst = np.maximum(worst, np.abs(_np(obs) - o)[:, :, 2:].max(axis=(1, 2)))
+    if precision == 'fp32':  # stiff contacts amplify fp32 rounding for as long as they last (see test_gpu_actor.py)
+        assert worst.max() <= 5e-4 and np.quantile(worst, 0.99) <= 5e-5 and np.median(worst) <= 2e-6, \
+            (worst.max(), np.quantile(worst, 0.99), np.median(worst))
+    assert n == 1 or contacts > 100
