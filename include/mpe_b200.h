@@ -208,6 +208,33 @@ int actor_forward_host_async(MpeActor *actor, const float *obs_host, int64_t B, 
 int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *obs_next, float *rew,
                 int32_t *act_u, int32_t *act_c, void *stream);
 
+/* ---- critic: rls/model/ac_network_multi_gumbel.py:70-148 (main.py path) and
+ * rls/model/ac_network_model_multi_gumbel.py:69-143 ("+model": extra reward head, no relu after the attention).
+ * Not on the acting path: evaluated by Trainer.optimize() at ddpg_gumbel_fix.py:151,159,191. ---- */
+typedef struct MpeCritic MpeCritic;
+typedef struct {
+  int32_t obs_dim;          /* D                                                           */
+  int32_t act_dim;          /* sum of the action head widths (input = D + act_dim, main.py:61) */
+  int32_t out_dim;          /* 1                                                           */
+  int32_t has_reward_head;  /* dense3 (ac_network_model_multi_gumbel.py:91,141)            */
+  int32_t relu_attention;   /* 1: relu on the attention output (ac_network_multi_gumbel.py:141), 0: "+model" critic */
+  int32_t device;
+} CriticConfig;
+/* HOST pointers to fp32 tensors in the reference's state_dict layout (row-major [out][in]). */
+typedef struct {
+  const float *dense1_w, *dense1_b;        /* [64][D + act_dim], [64]                    */
+  const float *w_ih, *w_hh, *b_ih, *b_hh;  /* lstm.*_l0: [256][64], [256][64], [256], [256] */
+  const float *dense2_w, *dense2_b;        /* [out_dim][64], [out_dim]                   */
+  const float *dense3_w, *dense3_b;        /* [out_dim][64], [out_dim] or NULL           */
+} CriticWeights;
+int critic_create(const CriticConfig *cfg, MpeCritic **out);
+int critic_destroy(MpeCritic *critic);
+int critic_load(MpeCritic *critic, const CriticWeights *w, void *stream);
+/* critic.forward(obs, action): obs [B][N][D], action [B][N][act_dim] fp32 (one-hot or soft; two heads concatenated
+ * like ac_network_multi_gumbel.py:131-132) -> q [B][out_dim] and, for the "+model" critic, r [B][out_dim] (or NULL). */
+int critic_forward(MpeCritic *critic, const float *obs, const float *action, int64_t B, int32_t N, float *q, float *r,
+                   void *stream);
+
 /* ---- device-resident replay ring: rls/replay_buffer.py:9-91 (ReplayBuffer), fed with the tuple of
  * experiments/run.py:46,52 (obs_n, action_n_env, rew_shared = sum(rew_n), new_obs_n, float(done)) ---- */
 typedef struct MpeReplay MpeReplay;

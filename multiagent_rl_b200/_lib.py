@@ -43,6 +43,16 @@ class ActorConfig(C.Structure):
                 ('has_model_head', C.c_int32), ('device', C.c_int32), ('reserved0', C.c_int32)]
 
 
+class CriticConfig(C.Structure):
+    _fields_ = [('obs_dim', C.c_int32), ('act_dim', C.c_int32), ('out_dim', C.c_int32), ('has_reward_head', C.c_int32),
+                ('relu_attention', C.c_int32), ('device', C.c_int32)]
+
+
+class CriticWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('dense1_w', 'dense1_b', 'w_ih', 'w_hh', 'b_ih', 'b_hh', 'dense2_w', 'dense2_b',
+                                          'dense3_w', 'dense3_b')]
+
+
 _WEIGHT_FIELDS = ['dense1_w', 'dense1_b', 'w_ih', 'w_hh', 'b_ih', 'b_hh', 'w_ih_r', 'w_hh_r', 'b_ih_r',
                   'b_hh_r', 'dense2_w', 'dense2_b', 'dense2b_w', 'dense2b_b', 'dense3_w', 'dense3_b']
 
@@ -85,6 +95,10 @@ SIGNATURES = {
     'actor_forward_host_async': (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, P, P, P,
                                            C.c_int32, P]),
     'mpe_rollout': (C.c_int, [P, P, C.c_int32, C.c_uint64, P, P, P, P, P]),
+    'critic_create': (C.c_int, [C.POINTER(CriticConfig), C.POINTER(P)]),
+    'critic_destroy': (C.c_int, [P]),
+    'critic_load': (C.c_int, [P, C.POINTER(CriticWeights), P]),
+    'critic_forward': (C.c_int, [P, P, P, C.c_int64, C.c_int32, P, P, P]),
     'replay_create': (C.c_int, [C.POINTER(ReplayConfig), C.POINTER(P)]),
     'replay_destroy': (C.c_int, [P]),
     'replay_clear': (C.c_int, [P]),

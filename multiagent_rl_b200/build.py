@@ -26,6 +26,7 @@ UNITS = [
     ('actor_kernels.cu', []),
     ('tc_kernels.cu', []),
     ('replay_kernels.cu', []),
+    ('critic_kernels.cu', []),
     ('cabi.cu', ['-Xcompiler', '-fvisibility=default']),
 ]
 

@@ -42,6 +42,8 @@ void actor_layout(int D, int A0, int A1, bool has_model, ActorDev *o) {
   o->off_b1 = off; off += kHid;
   o->off_w2 = off; off += kHid * o->Apad;
   o->off_b2 = off; off += o->Apad;
+  o->smem_floats = (size_t)round_up(off, 32);  // the dense3 head stays in global memory (L2): not on the acting path
+  off = (int)o->smem_floats;
   o->off_w3 = off; off += has_model ? kHid * o->Dpad : 0;
   o->off_b3 = off; off += has_model ? o->Dpad : 0;
   o->blob_floats = (size_t)round_up(off, 32);
@@ -297,7 +299,7 @@ __device__ __forceinline__ void actor_tile(const ActorDev &w, const ActorSmem<N,
         if (a < A) io.logits[row * A + a] = lg[a];
     }
     if (ok && io.next_state != nullptr) {  // dense3 head ("+model" actor), not on the acting path
-      const float *W3 = sm.w + w.off_w3, *b3 = sm.w + w.off_b3;
+      const float *W3 = w.blob + w.off_w3, *b3 = w.blob + w.off_b3;  // global (L2-resident), see actor_layout
       for (int j = 0; j < D; ++j) {
         float acc = b3[j];
         for (int k = 0; k < kHid; ++k) acc = fmaf(fmaxf(hrow[k * TBP], 0.0f), W3[k * w.Dpad + j], acc);
@@ -332,15 +334,15 @@ template <int N, int TB, int PAD>
 __global__ void __launch_bounds__(kActorThreads, 1) k_actor_forward(ActorDev w, ActorIO io, int64_t ntiles) {
   extern __shared__ __align__(128) float smem_f[];
   ActorSmem<N, TB, PAD> sm;
-  sm.carve(smem_f, w.blob_floats, w.D);
+  sm.carve(smem_f, w.smem_floats, w.D);
   const int tid = threadIdx.x;
   const int ND = N * w.D;
   if (tid == 0) {
     mbar_init(&sm.bars[0], 1);
     mbar_init(&sm.bars[1], 1);
     mbar_fence_init();
-    mbar_expect_tx(&sm.bars[0], (uint32_t)(w.blob_floats * sizeof(float)));
-    bulk_load(sm.w, w.blob, (uint32_t)(w.blob_floats * sizeof(float)), &sm.bars[0]);
+    mbar_expect_tx(&sm.bars[0], (uint32_t)(w.smem_floats * sizeof(float)));
+    bulk_load(sm.w, w.blob, (uint32_t)(w.smem_floats * sizeof(float)), &sm.bars[0]);
   }
   __syncthreads();
   uint32_t obs_phase = 0;
@@ -380,13 +382,13 @@ __global__ void __launch_bounds__(kActorThreads, 1)
   using Dm = Dims<SC, N>;
   constexpr int D = Dm::D, R = Dm::R;
   ActorSmem<N, TB, PAD> sm;
-  sm.carve(smem_f, w.blob_floats, D);
+  sm.carve(smem_f, w.smem_floats, D);
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&sm.bars[0], 1);
     mbar_fence_init();
-    mbar_expect_tx(&sm.bars[0], (uint32_t)(w.blob_floats * sizeof(float)));
-    bulk_load(sm.w, w.blob, (uint32_t)(w.blob_floats * sizeof(float)), &sm.bars[0]);
+    mbar_expect_tx(&sm.bars[0], (uint32_t)(w.smem_floats * sizeof(float)));
+    bulk_load(sm.w, w.blob, (uint32_t)(w.smem_floats * sizeof(float)), &sm.bars[0]);
   }
   __syncthreads();
   bool have_w = false;
@@ -524,6 +526,40 @@ __global__ void __launch_bounds__(kActorThreads, 1)
 #endif  // MPE_AB_KERNELS
 
 // ------------------------------------------------------------------------------------------------
+// dense3 head of the "+model" actor on top of the tensor-core forward: next_state[row][j] = b3[j] + sum_k
+// relu(hcat)[row][k] W3[k][j] (ac_network_model_multi_gumbel.py:49,65).  64 x D MACs per row - HBM-bound on reading
+// hcat (256 B per row), so a plain FFMA kernel: one thread per (row, output), the row's 64 inputs are broadcast loads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dense3(ActorDev w, const float *__restrict__ hcat, int64_t rows,
+                                                float *__restrict__ next_state) {
+  const int D = w.D;
+  const float *W3 = w.blob + w.off_w3, *b3 = w.blob + w.off_b3;
+  const int64_t total = rows * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / D;
+    const int j = (int)(i - row * D);
+    const float4 *h4 = reinterpret_cast<const float4 *>(hcat + row * kHid);
+    float acc = b3[j];
+#pragma unroll 4
+    for (int k4 = 0; k4 < kHid / 4; ++k4) {
+      const float4 h = h4[k4];
+      acc = fmaf(h.x, W3[(4 * k4) * w.Dpad + j], acc);
+      acc = fmaf(h.y, W3[(4 * k4 + 1) * w.Dpad + j], acc);
+      acc = fmaf(h.z, W3[(4 * k4 + 2) * w.Dpad + j], acc);
+      acc = fmaf(h.w, W3[(4 * k4 + 3) * w.Dpad + j], acc);
+    }
+    next_state[i] = acc;
+  }
+}
+
+cudaError_t launch_dense3(const ActorDev &w, const float *hcat, int64_t rows, float *next_state, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const int64_t blocks = (rows * w.D + 255) / 256;
+  k_dense3<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(w, hcat, rows, next_state);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
 bool actor_supported(int N) { return N >= 1 && N <= 12; }  // any team size make_env(n=...) is asked for, up to 12
@@ -540,7 +576,7 @@ static int sm_count() {
 
 template <int N, int TB, int PAD>
 static cudaError_t launch_actor_t(const ActorDev &w, const ActorIO &io, cudaStream_t st) {
-  const size_t smem = ActorSmem<N, TB, PAD>::bytes(w.blob_floats, w.D);
+  const size_t smem = ActorSmem<N, TB, PAD>::bytes(w.smem_floats, w.D);
   static size_t have[64] = {0};  // sticky per (kernel, device): raise the opt-in only when a launch needs more
   int dev = 0;
   cudaGetDevice(&dev);
@@ -577,7 +613,7 @@ cudaError_t launch_actor_forward(const ActorDev &w, const ActorIO &io, cudaStrea
 #ifdef MPE_AB_KERNELS
 template <int SC, int N, int TB, int PAD>
 static cudaError_t launch_rollout_t(const EnvStateAny &a, const ActorDev &w, const RolloutIO &ro, cudaStream_t st) {
-  const size_t smem = ActorSmem<N, TB, PAD>::bytes(w.blob_floats, w.D);
+  const size_t smem = ActorSmem<N, TB, PAD>::bytes(w.smem_floats, w.D);
   cudaError_t e = cudaFuncSetAttribute(k_rollout<SC, N, TB, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   EnvState<float> s;

@@ -34,6 +34,7 @@ struct ActorDev {
   int impl = kImplAuto;
   float *blob = nullptr;
   size_t blob_floats = 0;
+  size_t smem_floats = 0;  // leading part of the blob a CTA stages in shared memory (everything but the dense3 head)
   int D = 0, A0 = 0, A1 = 0, A = 0, Apad = 0, Dpad = 0, has_model = 0;
   int off_wg[2] = {0, 0};  // [96][128]
   int off_bg = 0;          // [2][128]
@@ -57,6 +58,7 @@ struct ActorIO {
   float *next_state = nullptr;    // [B][N][D]
   int32_t *act_u = nullptr, *act_c = nullptr;  // [B][N]
   float *onehot = nullptr;        // [B][N][A]
+  float *hcat = nullptr;          // [B][N][64] relu(BiLSTM output): tensor-core path only, feeds launch_dense3
   int64_t B = 0, gid0 = 0;
   int32_t N = 0;
   uint64_t seed = 0, step = 0;
@@ -83,6 +85,8 @@ bool tc_rollout_supported(const TcDev &w, int N);
 size_t tc_scratch_floats(int sm_count);
 cudaError_t launch_actor_forward_tc(const TcDev &w, const ActorIO &io, cudaStream_t st);
 cudaError_t launch_rollout_tc(const EnvStateAny &env, const TcDev &w, const RolloutIO &io, cudaStream_t st);
+// next_state = dense3(hcat): the "+model" head (ac_network_model_multi_gumbel.py:49,65) on top of the tensor-core forward
+cudaError_t launch_dense3(const ActorDev &w, const float *hcat, int64_t rows, float *next_state, cudaStream_t st);
 cudaError_t launch_rollout(const EnvStateAny &env, const ActorDev &w, const RolloutIO &io, cudaStream_t st);
 
 }  // namespace mpe

@@ -10,6 +10,7 @@
 
 #include "../../include/mpe_b200.h"
 #include "actor_launch.h"
+#include "critic_launch.h"
 #include "env_launch.h"
 #include "replay_launch.h"
 
@@ -79,6 +80,13 @@ struct MpeActor {
   mpe::ActorDev dev;
   int device = 0;
   ActorMirror mirror[kHostSlots];
+  float *hcat = nullptr;  // [rows][64] relu(BiLSTM output) between the tensor-core forward and the dense3 head
+  int64_t hcat_rows = 0;
+};
+
+struct MpeCritic {
+  mpe::CriticDev dev;
+  int device = 0;
 };
 
 struct MpeReplay {
@@ -361,7 +369,7 @@ int actor_destroy(MpeActor *a) {
   if (a == nullptr) return MPE_OK;
   DeviceGuard g(a->device);
   cudaDeviceSynchronize();
-  void *ptrs[] = {a->dev.blob, a->dev.tc.blob, a->dev.tc.scratch};
+  void *ptrs[] = {a->dev.blob, a->dev.tc.blob, a->dev.tc.scratch, a->hcat};
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
   for (ActorMirror &m : a->mirror) {
@@ -428,12 +436,25 @@ int actor_forward(MpeActor *a, const float *obs, int64_t B, int32_t N, const flo
   io.obs = obs; io.gumbel = gumbel; io.logits = logits; io.next_state = next_state;
   io.act_u = act_u; io.act_c = act_c; io.onehot = onehot;
   io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
-  if (a->dev.impl == mpe::kImplTc && !use_tc(a, N, next_state != nullptr))
-    return fail(MPE_EUNSUPPORTED, "actor_forward: the tensor-core path covers 2/3/4/6/9/12 agents, obs_dim <= 32, <= 8 head entries for > 3 agents, no model head");
-  if (use_tc(a, N, next_state != nullptr))
-    CK(mpe::launch_actor_forward_tc(a->dev.tc, io, static_cast<cudaStream_t>(stream)));
-  else
-    CK(mpe::launch_actor_forward(a->dev, io, static_cast<cudaStream_t>(stream)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->dev.impl == mpe::kImplTc && !use_tc(a, N, false))
+    return fail(MPE_EUNSUPPORTED, "actor_forward: the tensor-core path covers 2/3/4/6/9/12 agents, obs_dim <= 32, <= 8 head entries for > 3 agents");
+  if (use_tc(a, N, false)) {
+    if (next_state != nullptr) {  // "+model" head: the forward leaves relu(hcat) behind, one small kernel applies dense3
+      const int64_t rows = B * N;
+      if (rows > a->hcat_rows) {
+        if (a->hcat != nullptr) { CK(cudaStreamSynchronize(st)); cudaFree(a->hcat); a->hcat = nullptr; a->hcat_rows = 0; }
+        CK(cudaMalloc(&a->hcat, (size_t)rows * 64 * sizeof(float)));
+        a->hcat_rows = rows;
+      }
+      io.hcat = a->hcat;
+      io.next_state = nullptr;
+    }
+    CK(mpe::launch_actor_forward_tc(a->dev.tc, io, st));
+    if (next_state != nullptr) CK(mpe::launch_dense3(a->dev, a->hcat, B * N, next_state, st));
+  } else {
+    CK(mpe::launch_actor_forward(a->dev, io, st));
+  }
   return MPE_OK;
 }
 
@@ -630,6 +651,72 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
       }
     }
   }
+  return MPE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// critic
+// ------------------------------------------------------------------------------------------------
+int critic_destroy(MpeCritic *c);
+
+int critic_create(const CriticConfig *cfg, MpeCritic **out) {
+  if (cfg == nullptr || out == nullptr) return fail(MPE_EINVAL, "critic_create: null argument");
+  *out = nullptr;
+  if (cfg->obs_dim <= 0 || cfg->act_dim <= 0 || cfg->obs_dim + cfg->act_dim > mpe::kCriticMaxIn)
+    return fail(MPE_EUNSUPPORTED, "critic_create: obs_dim + act_dim out of range");
+  if (cfg->out_dim <= 0 || cfg->out_dim > mpe::kCriticMaxOut) return fail(MPE_EUNSUPPORTED, "critic_create: out_dim out of range");
+  DeviceGuard g(cfg->device);
+  if (!g.ok) return fail(MPE_ECUDA, "critic_create: cannot select device");
+  MpeCritic *c = new (std::nothrow) MpeCritic();
+  if (c == nullptr) return fail(MPE_EINVAL, "critic_create: out of host memory");
+  c->device = cfg->device;
+  mpe::critic_layout(cfg->obs_dim, cfg->act_dim, cfg->out_dim, cfg->has_reward_head != 0, cfg->relu_attention != 0, &c->dev);
+  cudaError_t e = cudaMalloc(&c->dev.blob, c->dev.blob_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(c->dev.blob, 0, c->dev.blob_floats * sizeof(float));
+  if (e != cudaSuccess) {
+    critic_destroy(c);
+    return fail_cuda(e, "critic_create: cudaMalloc");
+  }
+  *out = c;
+  return MPE_OK;
+}
+
+int critic_destroy(MpeCritic *c) {
+  if (c == nullptr) return MPE_OK;
+  DeviceGuard g(c->device);
+  cudaDeviceSynchronize();
+  if (c->dev.blob != nullptr) cudaFree(c->dev.blob);
+  delete c;
+  return MPE_OK;
+}
+
+int critic_load(MpeCritic *c, const CriticWeights *w, void *stream) {
+  if (c == nullptr || w == nullptr) return fail(MPE_EINVAL, "critic_load: null argument");
+  if (!w->dense1_w || !w->dense1_b || !w->w_ih || !w->w_hh || !w->b_ih || !w->b_hh || !w->dense2_w || !w->dense2_b)
+    return fail(MPE_EINVAL, "critic_load: missing tensor");
+  if (c->dev.has_r && (!w->dense3_w || !w->dense3_b)) return fail(MPE_EINVAL, "critic_load: missing dense3");
+  DeviceGuard g(c->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float *host = nullptr;
+  CK(cudaMallocHost(&host, c->dev.blob_floats * sizeof(float)));
+  mpe::CriticHostWeights hw = {w->dense1_w, w->dense1_b, w->w_ih, w->w_hh, w->b_ih, w->b_hh,
+                               w->dense2_w, w->dense2_b, w->dense3_w, w->dense3_b};
+  mpe::critic_pack(c->dev, hw, host);
+  cudaError_t e = cudaMemcpyAsync(c->dev.blob, host, c->dev.blob_floats * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the pinned staging buffer is freed below
+  cudaFreeHost(host);
+  if (e != cudaSuccess) return fail_cuda(e, "critic_load: upload");
+  return MPE_OK;
+}
+
+int critic_forward(MpeCritic *c, const float *obs, const float *action, int64_t B, int32_t N, float *q, float *r,
+                   void *stream) {
+  if (c == nullptr || obs == nullptr || action == nullptr || q == nullptr) return fail(MPE_EINVAL, "critic_forward: null argument");
+  if (B <= 0) return MPE_OK;
+  if (N < 1 || N > mpe::kCriticMaxAgents) return fail(MPE_EUNSUPPORTED, "critic_forward: 1..16 agents");
+  if (r != nullptr && !c->dev.has_r) return fail(MPE_EINVAL, "critic_forward: no reward head loaded");
+  DeviceGuard g(c->device);
+  CK(mpe::launch_critic_forward(c->dev, obs, action, B, N, q, r, static_cast<cudaStream_t>(stream)));
   return MPE_OK;
 }
 

@@ -227,7 +227,8 @@ __device__ __forceinline__ f2 rcp2_newton(f2 d) {
 // Writes h as an fp16 hi/lo K-chunk of the recurrent A operand when `store_h`.
 template <int APAD>
 __device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float *bg, const float *w2rows, f2 (&c)[4],
-                                           f2 (&pl)[APAD / 2], unsigned char *h_chunk, int row, bool store_h) {
+                                           f2 (&pl)[APAD / 2], unsigned char *h_chunk, int row, bool store_h,
+                                           float *hcat8 = nullptr) {
   const f2 ONE = pk(1.0f, 1.0f), NEG1 = pk(-1.0f, -1.0f);
   const f2 S1 = pk(-kWInv * kLog2e, -kWInv * kLog2e), S2 = pk(-2.0f * kWInv * kLog2e, -2.0f * kWInv * kLog2e);
   const f2 S3 = pk(-2.0f * kLog2e, -2.0f * kLog2e);
@@ -273,6 +274,10 @@ __device__ __forceinline__ void lstm_chunk(const uint32_t (&v)[32], const float 
     }
   }
   if (store_h) store_chunk_split(h_chunk, h_chunk + 8192, row, hv);
+  if (hcat8 != nullptr) {  // relu(h) of these 8 units for the dense3 head (actor_forward with next_state; 32 B aligned)
+    *reinterpret_cast<float4 *>(hcat8) = make_float4(fmaxf(hv[0], 0.0f), fmaxf(hv[1], 0.0f), fmaxf(hv[2], 0.0f), fmaxf(hv[3], 0.0f));
+    *reinterpret_cast<float4 *>(hcat8 + 4) = make_float4(fmaxf(hv[4], 0.0f), fmaxf(hv[5], 0.0f), fmaxf(hv[6], 0.0f), fmaxf(hv[7], 0.0f));
+  }
 }
 
 #ifdef MPE_AB_KERNELS  // the superseded two-pipeline kernel: A/B builds only (python -m multiagent_rl_b200.build --variant ab MPE_AB_KERNELS)
@@ -1086,16 +1091,26 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
           tc_fence_after();
           TS(4);
           {
+            // dense3 head requested (actor_forward with next_state): relu(h) of this thread's 16 units goes to
+            // hcat[env][agent][dir * 32 + unit]; rows beyond the batch are skipped
+            float *hc = nullptr;
+            if constexpr (!FUSED) {
+              if (io.hcat != nullptr) {
+                const int64_t bx = (pair * 2 + X) * (int64_t)kRows + row;
+                if (bx < io.B) hc = io.hcat + (bx * N + (d == 0 ? st : N - 1 - st)) * kHid + d * kH + half * 16;
+              }
+            }
             uint32_t va[32], vb[32];
             tmem_ld32(tmem + lane_base + half * 64, va);
             tmem_wait_ld();
             TS(5);
             tmem_ld32(tmem + lane_base + half * 64 + 32, vb);  // in flight during the first chunk's math
-            lstm_chunk<APAD>(va, bg, w2d, c[0], pl, sm_h + (2 * half) * kChunkA, row, st < N - 1);
+            lstm_chunk<APAD>(va, bg, w2d, c[0], pl, sm_h + (2 * half) * kChunkA, row, st < N - 1, hc);
             TS(6);
             tmem_wait_ld();
             TS(7);
-            lstm_chunk<APAD>(vb, bg + 32, w2d + 8 * 16, c[1], pl, sm_h + (2 * half + 1) * kChunkA, row, st < N - 1);
+            lstm_chunk<APAD>(vb, bg + 32, w2d + 8 * 16, c[1], pl, sm_h + (2 * half + 1) * kChunkA, row, st < N - 1,
+                             hc != nullptr ? hc + 8 : nullptr);
           }
           fence_proxy_async_smem();
           tc_fence_before();

@@ -11,6 +11,7 @@ Two families:
     implementation of the physics exists in /root/reference (it imports the
     un-vendored ``multiagent`` package), so these pin the *restatement*, not
     the reference: parity unpinned.
+  * ``critic_*.npz`` - outputs of the REFERENCE's own CriticNetwork classes (same two files, :70-148 / :69-143).
   * ``actor_*.npz`` - outputs of the REFERENCE's own ActorNetwork
     (/root/reference/rls/model/ac_network_multi_gumbel.py:24-67 and
     ac_network_model_multi_gumbel.py:23-66) and of the reference's sampling
@@ -133,6 +134,42 @@ def gen_actor(tag, D, A, N, B, seed, model_head):
     print('wrote', name)
 
 
+def gen_critic(tag, D, A, N, B, seed, model):
+    """Outputs of the REFERENCE's own CriticNetwork (rls/model/ac_network_multi_gumbel.py:70-148 or
+    ac_network_model_multi_gumbel.py:69-143) on seeded observations and one-hot / soft actions."""
+    sys.path.insert(0, '/root/reference')
+    import torch
+    import torch.nn.functional as F
+    if model:
+        from rls.model.ac_network_model_multi_gumbel import CriticNetwork
+    else:
+        from rls.model.ac_network_multi_gumbel import CriticNetwork
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    widths = A if isinstance(A, list) else [A]
+    critic = CriticNetwork(input_dim=D + int(np.sum(widths)), out_dim=1)   # main.py:61
+    obs = np.random.uniform(-1.5, 1.5, (B, N, D)).astype(np.float32)
+    acts = []
+    for w in widths:  # half the rows exact one-hots (replay), half soft Gumbel-softmax samples (optimize())
+        logits = torch.randn(B, N, w)
+        soft = F.gumbel_softmax(logits.view(B * N, w), hard=False).view(B, N, w)
+        hard = F.one_hot(logits.argmax(-1), w).float()
+        a = torch.where((torch.arange(B) % 2 == 0).view(B, 1, 1), hard, soft)
+        acts.append(a.numpy().astype(np.float32))
+    with torch.no_grad():
+        res = critic.forward(torch.from_numpy(obs), [torch.from_numpy(a) for a in acts] if len(acts) > 1 else torch.from_numpy(acts[0]))
+    out = {'obs': obs, 'action': np.concatenate(acts, -1)}
+    for k, v in critic.state_dict().items():
+        out['sd/' + k] = v.numpy()
+    if model:
+        out['q'], out['r'] = res[0].numpy(), res[1].numpy()
+    else:
+        out['q'] = res.numpy()
+    name = 'critic_%s.npz' % tag
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print('wrote', name)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     gen_mpe('simple_spread', None, 48, 101)
@@ -147,6 +184,9 @@ def main():
         gen_actor('reference', 21, [5, 10], 2, 256, 12345680, False)
         gen_actor('speaker', 11, 5, 2, 256, 12345681, False)
         gen_actor('model_n6', 16, 5, 6, 64, 12345682, True)
+        gen_critic('spread_n3', 10, 5, 3, 256, 12345683, False)
+        gen_critic('reference', 21, [5, 10], 2, 256, 12345684, False)
+        gen_critic('model_n12', 28, 5, 12, 64, 12345685, True)
     else:
         print('no /root/reference: actor fixtures not regenerated')
 

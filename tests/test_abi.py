@@ -12,7 +12,7 @@ from tests.conftest import ROOT
 def _header_functions():
     src = open(os.path.join(ROOT, 'include', 'mpe_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    names = re.findall(r'^\s*(?:const\s+char\s*\*|int64_t|int)\s*\*?\s*((?:mpe|actor|replay)_\w+)\s*\(', src, flags=re.M)
+    names = re.findall(r'^\s*(?:const\s+char\s*\*|int64_t|int)\s*\*?\s*((?:mpe|actor|critic|replay)_\w+)\s*\(', src, flags=re.M)
     return sorted(set(names))
 
 
@@ -38,6 +38,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.MpeDims) == 48
     assert ctypes.sizeof(_lib.ActorConfig) == 24
     assert ctypes.sizeof(_lib.ActorWeights) == 16 * 8
+    assert ctypes.sizeof(_lib.CriticConfig) == 24 and ctypes.sizeof(_lib.CriticWeights) == 10 * 8
+    assert ctypes.sizeof(_lib.MpeHostBlockLayout) == 48
 
 
 def test_argument_errors_do_not_need_a_gpu():

@@ -29,9 +29,7 @@ def _load(golden_dir, tag):
 
 def _impls(N, model=False, wide=False):
     # tensor-core path: 2-3 agents (resident operands, fused env), 4/6/9/12 agents (just-in-time operands, single
-    # head of <= 8 entries); the dense3 model head stays on the fp32 SIMT kernel
-    if model:
-        return ['simt']
+    # head of <= 8 entries); the dense3 model head is one small kernel on the relu(hcat) the tensor-core forward emits
     if N in (2, 3) or (N in (4, 6, 9, 12) and not wide):
         return ['simt', 'tc']
     return ['simt']
@@ -437,3 +435,20 @@ def test_actor_and_rollout_for_every_team_size(n):
         assert torch.equal(o, rec[0][t]) and torch.equal(rew, rec[1][t]), t
         if (t + 1) % L == 0:
             o = env2.reset()
+
+
+@pytest.mark.parametrize('N,D,B', [(3, 10, 1000), (2, 21, 129), (6, 16, 4097), (12, 28, 300)])
+def test_model_head_next_state_on_both_paths(N, D, B):
+    """ac_network_model_multi_gumbel.py:49,65: next_state = dense3(relu(hcat)).  The tensor-core forward emits
+    relu(hcat) and one small kernel applies dense3; the fp32 FFMA kernel computes it in place.  Both vs the float64
+    restatement (1e-5), at batch sizes that leave the last tile partly empty."""
+    import multiagent_rl_b200 as m
+    sd = actor_ref.init_state_dict(D, 5, 4, model_head=True)
+    for k in sd:
+        sd[k] = sd[k] * 2.0
+    obs = np.random.RandomState(N).uniform(-2, 2, (B, N, D)).astype(np.float32)
+    want = actor_ref.forward(sd, obs)
+    for impl in ('tc', 'simt'):
+        out = m.FusedActor(sd, impl=impl).forward(torch.from_numpy(obs), want_next_state=True, want_logits=True)
+        assert np.abs(out['next_state'].cpu().numpy() - want['next_state']).max() <= LOGIT_ATOL * 2, impl
+        assert np.abs(out['logits'].cpu().numpy() - want['logits'][0]).max() <= LOGIT_ATOL * 2, impl

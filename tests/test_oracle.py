@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import actor_ref, mpe_ref, mpe_vec, philox
+from oracle import actor_ref, critic_ref, mpe_ref, mpe_vec, philox
 
 MPE_FILES = [('simple_spread', None), ('simple_spread', 6), ('simple_spread', 9), ('simple_spread', 12),
              ('simple_reference', None), ('simple_speaker_listener', None)]
@@ -207,3 +207,15 @@ def test_replay_restatement_matches_reference_class():
     idx = [0, 6, 3, 3, 1]
     for a, b in zip(ref.sample_index(idx), mine.sample_index(idx)):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('tag', ['spread_n3', 'reference', 'model_n12'])
+def test_critic_restatement_matches_reference_network(golden_dir, tag):
+    """tests/golden/critic_*.npz are outputs of the reference's CriticNetwork classes (fp32, CPU)."""
+    g = np.load(os.path.join(golden_dir, 'critic_%s.npz' % tag))
+    sd = {k[3:]: g[k] for k in g.files if k.startswith('sd/')}
+    out = critic_ref.forward(sd, g['obs'], g['action'])
+    assert out['q'].shape == g['q'].shape and np.abs(out['q'] - g['q']).max() < 1e-6
+    assert ('r' in out) == ('r' in g.files)
+    if 'r' in out:
+        assert np.abs(out['r'] - g['r']).max() < 1e-6
