@@ -28,7 +28,13 @@ BYTES_PER_ENV_STEP = 41 * 3 + 8 * 3 + 4 * 3 * 10
 # algorithmic FLOPs of one actor forward per env: N (128 D + 49152 + 128 A)
 # DRAM traffic per launch of the two kernels the rooflines are quoted for, from the committed ncu --set full captures
 NCU_DRAM_BYTES_FUSED = 5.455e6   # k_tc2<0,3,1,8>, 65,536 envs: 5.455 MB read + 0 written (outputs stay in the 126 MB L2)
-NCU_DRAM_BYTES_STEP = 221.9e6    # k_step<float,0,3>, 1,048,576 envs: 88.1 MB read + 133.8 MB written (algorithmic 280 MB)
+NCU_DRAM_BYTES_STEP = 221.9e6    # k_step<float,0,3>, 1,048,576 envs, rotating outputs: 88.1 MB read + 133.8 MB written
+#   inside the kernel's window (algorithmic 88 + 192 MB: ~58 MB of dirty lines are still in L2 when the kernel ends
+#   and ncu flushes before the next replay; back to back they are written during the next launch)
+# MUFU (XU pipe) warp instructions per launch of k_tc2<0,3,1,8> at 65,536 envs: smsp__inst_executed_pipe_xu.sum in
+# profiles/r2_ncu_tc2_counters.txt = 989 transcendental evaluations per env step; XU issue rate 0.5 warp inst / clk / SM
+NCU_XU_WARP_INST_FUSED = 2025472
+XU_WARP_INST_PER_CLK_PER_SM = 0.5
 FLOPS_PER_ENV_STEP = N_AGENTS * (128 * OBS_DIM + 49152 + 128 * ACT_DIM)
 FP32_SIMT_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # FFMA peak at max clock (not a measured number)
 
@@ -63,8 +69,12 @@ def cpu_loop(n_env_steps, seed, threads=1):
     """Runs the reference-shaped rollout loop on the CPU oracle; returns (agent_steps, seconds)."""
     import torch
     import torch.nn.functional as F
-    from multiagent_rl_b200.networks import ActorNetwork
-    from oracle import mpe_ref
+    from oracle import build_ref, mpe_ref
+    if build_ref.available():  # the reference's own ActorNetwork (rls/model/ac_network_multi_gumbel.py:24-67), compiled
+        build_ref.add_to_path()  # into oracle/_ref by `python -m oracle.build_ref`
+        from rls.model.ac_network_multi_gumbel import ActorNetwork
+    else:
+        from multiagent_rl_b200.networks import ActorNetwork  # same layers and parameter names, this repo's mirror
     torch.set_num_threads(threads)
     np.random.seed(seed)
     torch.manual_seed(seed)
@@ -93,6 +103,12 @@ def _cpu_worker(args):
     return cpu_loop(n, seed, threads=1)
 
 
+def _cpu_actor_kind():
+    """Which ActorNetwork cpu_loop imports: the reference's own class when oracle/_ref was built."""
+    have = os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'rls', 'model', 'ac_network_multi_gumbel.refpyc'))
+    return 'reference ActorNetwork (oracle/_ref)' if have else 'torch mirror of the reference ActorNetwork'
+
+
 def cpu_baseline(seconds):
     """1 core, bounded sample of the same workload (rank 0, N = 1 only)."""
     cpu_loop(100, SEED)  # warm-up
@@ -100,8 +116,8 @@ def cpu_baseline(seconds):
     n = max(500, int(300 * seconds / max(dt, 1e-6)))
     steps, dt = cpu_loop(n, SEED)
     return {'value': steps / dt, 'unit': 'agent-steps/s', 'cores': 1, 'kind': 'port',
-            'sample': '%d env steps (25-step episodes) of the float64 loop oracle + torch CPU actor + '
-                      'F.gumbel_softmax, 1 thread, %.1f s' % (n, dt)}
+            'sample': '%d env steps (25-step episodes) of the float64 loop oracle + %s on torch CPU + '
+                      'F.gumbel_softmax, 1 thread, %.1f s' % (n, _cpu_actor_kind(), dt)}
 
 
 def run_reference(args):
@@ -135,7 +151,8 @@ def run_reference(args):
                                '(experiments/run.py:36-65), %d independent CPU processes x %d env steps per bench step'
                                % (cores, per_step)},
         'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d processes x %d steps x %d env steps' % (cores, args.steps, per_step)},
+                         'sample': '%d processes x %d steps x %d env steps; env = float64 loop oracle (the physics package '
+                                   'is not in the reference tree), actor = %s' % (cores, args.steps, per_step, _cpu_actor_kind())},
         'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -388,7 +405,13 @@ def run_b200(args):
                      'unit': 'TFLOP/s', 'frac': tflops / pk['bf16_tflops_sustained'],
                      'traffic': NCU_DRAM_BYTES_FUSED if B == 65536 else None,
                      'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch at 65,536 envs, '
-                                       'profiles/r1_ncu_full_summary_v8.txt (state + weights in, outputs stay in L2)',
+                                       'profiles/r2_ncu_full_summary_tc2_step.txt (state + weights in, outputs stay in L2)',
+                     'xu_frac': (NCU_XU_WARP_INST_FUSED / kernel_s) / (148 * XU_WARP_INST_PER_CLK_PER_SM * (clk.get('sm_mhz') or 1965.0) * 1e6)
+                                if B == 65536 else None,
+                     'xu_source': 'smsp__inst_executed_pipe_xu.sum = 2,025,472 warp instructions per launch (989 MUFU ops per '
+                                  'env step), profiles/r2_ncu_tc2_counters.txt; peak = 0.5 warp inst/clk/SM x 148 SMs x the SM '
+                                  'clock sampled during the run (ncu itself reads 25.9 % of XU peak over the CTA-active cycles, '
+                                  'tensor pipe 21.4 %, issue slots 41.9 % cold / 52.8 % warm)',
                      'kernel': 'k_tc2<simple_spread,3,fused> (tcgen05 kind::f16, fp16 hi/lo split operands, fp32 TMEM accum)',
                      'peak_source': pk['source'] + ' bf16 sustained',
                      'flops_per_env_step': FLOPS_PER_ENV_STEP,
@@ -449,23 +472,32 @@ def side_measurements(m, actor, dev, pk, off):
     env = m.make_env(SCENARIO, num_envs=B, batched=True, seed=SEED, env_id_offset=off)
     env.reset()
     act = torch.randint(0, 5, (B, N_AGENTS), dtype=torch.int32, device=dev)
-    bufs = (torch.empty((B, N_AGENTS, OBS_DIM), device=dev), torch.empty((B, N_AGENTS), device=dev),
-            torch.empty((B, N_AGENTS), dtype=torch.uint8, device=dev))
-    for _ in range(5):
-        env.step(act, out=bufs)
+    # four rotating output sets (566 MB > the 126 MB L2): every launch's obs / rew / done lines really go to DRAM
+    # instead of being overwritten in L2 by the next launch
+    rot = [(torch.empty((B, N_AGENTS, OBS_DIM), device=dev), torch.empty((B, N_AGENTS), device=dev),
+            torch.empty((B, N_AGENTS), dtype=torch.uint8, device=dev)) for _ in range(4)]
+    bufs = rot[0]
+    for i in range(8):
+        env.step(act, out=rot[i % 4])
     torch.cuda.synchronize()
-    reps = 50
+    reps = 48
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        env.step(act, out=bufs)  # 280 MB working set per launch > L2
+    for i in range(reps):
+        env.step(act, out=rot[i % 4])  # 280 MB of algorithmic traffic per launch, outputs rotate over 566 MB
     e1.record()
     torch.cuda.synchronize()
     s = e0.elapsed_time(e1) * 1e-3 / reps
     gbs = B * BYTES_PER_ENV_STEP / s / 1e9
     out['roofline_env_step'] = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                                 'frac': gbs / pk['hbm_gbs'], 'traffic': NCU_DRAM_BYTES_STEP,
-                                'traffic_source': 'profiles/r1_ncu_full_summary_v5.txt, 1,048,576 envs per launch',
+                                'frac_dram': NCU_DRAM_BYTES_STEP / s / 1e9 / pk['hbm_gbs'],
+                                'traffic_source': 'profiles/r2_ncu_full_summary_tc2_step.txt, 1,048,576 envs per launch, '
+                                                  'rotating outputs: 88.1 MB read + 133.8 MB written inside the kernel window; '
+                                                  'the remaining ~58 MB of the 192 MB of output are dirty L2 lines written '
+                                                  'back after the kernel ends (ncu flushes between replays), so frac_dram is a '
+                                                  'lower bound of the DRAM rate and frac (algorithmic bytes) the steady-state one',
+                                'outputs': '4 rotating sets, 566 MB > L2',
                                 'kernel': 'k_step<float,simple_spread,3>',
                                 'envs': B, 'agent_steps_per_s': B * N_AGENTS / s, 'us_per_launch': s * 1e6,
                                 'bytes_per_env_step': BYTES_PER_ENV_STEP, 'peak_source': pk['source']}

@@ -18,10 +18,12 @@ if which in ('all', 'step'):
     env = m.make_env('simple_spread', num_envs=B, batched=True, seed=1)
     env.reset()
     act = torch.randint(0, 5, (B, 3), dtype=torch.int32, device=dev)
-    out = (torch.empty((B, 3, 10), device=dev), torch.empty((B, 3), device=dev),
-           torch.empty((B, 3), dtype=torch.uint8, device=dev))
-    for _ in range(5):
-        env.step(act, out=out)
+    # four rotating output sets (566 MB > the 126 MB L2): a launch's output lines are written back to DRAM instead of
+    # being overwritten in L2 by the next launch, so ncu's dram__bytes is the traffic the byte model counts
+    outs = [(torch.empty((B, 3, 10), device=dev), torch.empty((B, 3), device=dev),
+             torch.empty((B, 3), dtype=torch.uint8, device=dev)) for _ in range(4)]
+    for i in range(8):
+        env.step(act, out=outs[i % 4])
     torch.cuda.synchronize()
 if which in ('all', 'rollout', 'actor'):
     B = 65536
