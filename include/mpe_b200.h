@@ -175,7 +175,9 @@ int actor_destroy(MpeActor *actor);
 int actor_load(MpeActor *actor, const ActorWeights *w, void *stream);
 
 /* Implementation of the actor GEMMs: 0 = auto (tensor cores where supported), 1 = fp32 SIMT (FFMA),
- * 2 = tcgen05 tensor cores with fp16 hi/lo split operands (fp32-level accuracy; 2-3 agents). */
+ * 2 = tcgen05 tensor cores with fp16 hi/lo split operands (fp32-level accuracy; 2/3/4/6/9/12 agents),
+ * 3 = like 2, and mpe_rollout runs teams of 6 / 9 / 12 agents as ONE kernel for all T steps instead of actor + step
+ *     kernels per step (same results bit for bit; measured slower at large batches, fewer launches at small ones). */
 int actor_set_impl(MpeActor *actor, int32_t impl);
 
 /* Trainer.get_exploration_action - rls/agent/multiagent/ddpg_gumbel_fix.py:86-107:

@@ -27,7 +27,7 @@ struct TcDev {
   float *scratch = nullptr;  // [148*2 pipelines][12 agents][16][128] forward-pass logits shares (teams of > 3 agents)
 };
 
-enum { kImplAuto = 0, kImplSimt = 1, kImplTc = 2 };
+enum { kImplAuto = 0, kImplSimt = 1, kImplTc = 2, kImplTcFusedLarge = 3 };
 
 struct ActorDev {
   TcDev tc;
@@ -70,6 +70,7 @@ struct RolloutIO {
   float *obs_next = nullptr;  // [T][B][N][D]
   float *rew = nullptr;       // [T][B][N]
   int32_t *act_u = nullptr, *act_c = nullptr;  // [T][B][N]
+  float *obs_work = nullptr;  // [B][N][D] large teams: holds the current observations on entry, rewritten every step
 };
 
 void actor_layout(int D, int A0, int A1, bool has_model, ActorDev *out);

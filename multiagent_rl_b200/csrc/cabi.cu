@@ -419,7 +419,7 @@ static bool use_tc(const MpeActor *a, int N, bool needs_simt) {
 }
 
 int actor_set_impl(MpeActor *a, int32_t impl) {
-  if (a == nullptr || impl < 0 || impl > 2) return fail(MPE_EINVAL, "actor_set_impl: bad argument");
+  if (a == nullptr || impl < 0 || impl > 3) return fail(MPE_EINVAL, "actor_set_impl: bad argument");
   a->dev.impl = impl;
   return MPE_OK;
 }
@@ -437,7 +437,7 @@ int actor_forward(MpeActor *a, const float *obs, int64_t B, int32_t N, const flo
   io.act_u = act_u; io.act_c = act_c; io.onehot = onehot;
   io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a->dev.impl == mpe::kImplTc && !use_tc(a, N, false))
+  if ((a->dev.impl == mpe::kImplTc || a->dev.impl == mpe::kImplTcFusedLarge) && !use_tc(a, N, false))
     return fail(MPE_EUNSUPPORTED, "actor_forward: the tensor-core path covers 2/3/4/6/9/12 agents, obs_dim <= 32, <= 8 head entries for > 3 agents");
   if (use_tc(a, N, false)) {
     if (next_state != nullptr) {  // "+model" head: the forward leaves relu(hcat) behind, one small kernel applies dense3
@@ -602,8 +602,21 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mpe::RolloutIO io;
   io.T = T; io.step0 = step0; io.obs_next = obs_next; io.rew = rew; io.act_u = act_u; io.act_c = act_c;
-  if (actor->dev.impl != mpe::kImplSimt && mpe::tc_rollout_supported(actor->dev.tc, env->st.N)) {
-    CK(mpe::launch_rollout_tc(env->st, actor->dev.tc, io, st));  // one kernel for all T steps (teams of <= 3)
+  // One kernel for all T steps: teams of <= 3.  For the large simple_spread teams (6 / 9 / 12) the single-kernel form
+  // exists too but is 17 - 20 % SLOWER than actor + step kernels per step (measured, DESIGN.md 4.3: the env step wants
+  // the whole GPU's occupancy, inside the persistent actor kernel it runs on 8 warps per SM), so it is opt-in.
+  if (actor->dev.impl != mpe::kImplSimt && mpe::tc_rollout_supported(actor->dev.tc, env->st.N) &&
+      (env->st.N <= 3 || actor->dev.impl == mpe::kImplTcFusedLarge)) {
+    if (env->st.N > 3) {  // large teams: the kernel streams the observations from a work buffer it rewrites every step
+      const int64_t rows = env->st.B * env->st.N;
+      if (env->r_obs == nullptr) {
+        CK(cudaMalloc(&env->r_obs, (size_t)rows * env->st.D * sizeof(float)));
+        CK(cudaMalloc(&env->r_act, (size_t)rows * 2 * sizeof(int32_t)));
+      }
+      CK(mpe::launch_observe(env->st, env->r_obs, st));
+      io.obs_work = env->r_obs;
+    }
+    CK(mpe::launch_rollout_tc(env->st, actor->dev.tc, io, st));
     env->synced = false;
     return MPE_OK;
   }

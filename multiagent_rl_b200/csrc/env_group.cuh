@@ -18,6 +18,15 @@
 
 namespace mpe {
 
+constexpr int kGroupStepThreads = 128;  // block size of k_step_grp / k_reset_grp (== kStepThreads of env_kernels.cuh)
+
+// Team size -> kernel family.  Up to 5 agents: one thread per env (every entity in registers).  6 and more: G lanes
+// per env, each owning N / G agents and landmarks; G is the divisor of N that keeps a lane at <= 3 agents with the
+// most envs per warp (primes get one agent per lane).
+__host__ __device__ constexpr int group_lanes(int N) {
+  return N <= 5 ? 0 : N == 6 ? 2 : N == 7 ? 7 : N == 8 ? 4 : N == 9 ? 3 : N == 10 ? 5 : N == 11 ? 11 : N == 12 ? 4 : -1;
+}
+
 template <typename T, int N, int G>
 struct GroupLayout {
   static constexpr int A = N / G;       // agents (and landmarks) per lane
@@ -40,7 +49,7 @@ struct GroupLayout {
   static constexpr bool kPerEnv = kPad != 0;
   static constexpr int RS = R + kPad;
   static constexpr int kWarpBytes = ((EPW * RS + EPW * N) * (int)sizeof(T) + 127) / 128 * 128;
-  static constexpr int kBlockBytes = kWarpBytes * (kStepThreads / 32);
+  static constexpr int kBlockBytes = kWarpBytes * (kGroupStepThreads / 32);
   static_assert(N % G == 0, "agents must split evenly over the lanes of an env");
 };
 
@@ -68,9 +77,10 @@ __device__ __forceinline__ bool grp_emit(const GroupLanes<T, N, G> &g, const T (
   constexpr int RS = GL::RS;
   T *st_obs = reinterpret_cast<T *>(smem + warp * GL::kWarpBytes);
   T *st_rew = st_obs + EPW * RS;
-  const bool obs_tma = full && obs != nullptr && (reinterpret_cast<uintptr_t>(obs + b0 * R) & 15) == 0 &&
+  // smem == nullptr: no staging buffer (the fused rollout's env phase) - rows go straight to global memory
+  const bool obs_tma = smem != nullptr && full && obs != nullptr && (reinterpret_cast<uintptr_t>(obs + b0 * R) & 15) == 0 &&
                        (GL::kPerEnv || (EPW * R * sizeof(T)) % 16 == 0);
-  const bool rew_tma = full && rew != nullptr && (reinterpret_cast<uintptr_t>(rew + b0 * N) & 15) == 0 &&
+  const bool rew_tma = smem != nullptr && full && rew != nullptr && (reinterpret_cast<uintptr_t>(rew + b0 * N) & 15) == 0 &&
                        ((EPW * N * sizeof(T)) % 16 == 0);
   if (obs != nullptr && obs_tma && GL::kVec > 1) {
     // shared-memory staging with vector stores (the pointer is derived from the shared array only, so these are STS)
@@ -162,30 +172,16 @@ __device__ __forceinline__ bool grp_emit(const GroupLanes<T, N, G> &g, const T (
   return issued;
 }
 
-template <typename T, int N, int G>
-__global__ void __launch_bounds__(kStepThreads)
-    k_step_grp(EnvState<T> s, const int32_t *__restrict__ act_u, T *__restrict__ obs, T *__restrict__ rew,
-               uint8_t *__restrict__ done, int32_t *__restrict__ info_i, T *__restrict__ info_f) {
-  using GL = GroupLayout<T, N, G>;
-  constexpr int A = GL::A, EPW = GL::EPW, L = N;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int el = lane / G, q = lane - el * G;            // env within the warp, lane within the env
-  const int base_lane = el * G;
-  const int64_t b0 = ((int64_t)blockIdx.x * (kStepThreads / 32) + warp) * EPW;
-  const int64_t b = b0 + el;
-  const bool lane_ok = lane < GL::LANES;
-  const bool active = lane_ok && b < s.B;
-  const bool full = b0 + EPW <= s.B;
-  const unsigned FULL = 0xffffffffu;
+// ---- pieces of the step shared by k_step_grp and the fused large-team rollout (tc_kernels.cu): every function below
+// ---- must be called by all 32 lanes of the warp (warp shuffles), `q` = lane within the env, `base_lane` = its first lane
 
-  T px[A], py[A], vx[A], vy[A], lx[A], ly[A];
-  int au[A];
+// the lane's agents and landmarks of env b (SoA state); inactive lanes keep zeros
+template <typename T, int N, int G>
+__device__ __forceinline__ void grp_load(const EnvState<T> &s, int64_t b, int q, bool active, T (&px)[N / G], T (&py)[N / G],
+                                         T (&vx)[N / G], T (&vy)[N / G], T (&lx)[N / G], T (&ly)[N / G]) {
+  constexpr int A = N / G;
 #pragma unroll
-  for (int k = 0; k < A; ++k) {
-    px[k] = py[k] = vx[k] = vy[k] = lx[k] = ly[k] = (T)0;
-    au[k] = 0;
-  }
+  for (int k = 0; k < A; ++k) px[k] = py[k] = vx[k] = vy[k] = lx[k] = ly[k] = (T)0;
   if (active) {
 #pragma unroll
     for (int k = 0; k < A; ++k) {
@@ -194,11 +190,16 @@ __global__ void __launch_bounds__(kStepThreads)
       px[k] = v.x; py[k] = v.y; vx[k] = v.z; vy[k] = v.w;
       const Vec2<T> l = ld2(s.lm + ((int64_t)i * s.B + b) * 2);
       lx[k] = l.x; ly[k] = l.y;
-      au[k] = act_u[b * N + i];
     }
   }
+}
 
-  // ---- _set_action + apply_environment_force on the lane's own agents ----
+// _set_action + apply_environment_force on the lane's own agents + integrate_state
+template <typename T, int N, int G>
+__device__ __forceinline__ void grp_physics(const EnvState<T> &s, const int (&au)[N / G], int q, int base_lane,
+                                            T (&px)[N / G], T (&py)[N / G], T (&vx)[N / G], T (&vy)[N / G]) {
+  constexpr int A = N / G;
+  const unsigned FULL = 0xffffffffu;
   const T sens = s.accel >= (T)0 ? s.accel : (T)5.0;
   T fx[A], fy[A];
 #pragma unroll
@@ -225,17 +226,19 @@ __global__ void __launch_bounds__(kStepThreads)
       }
     }
   }
-  // ---- integrate_state ----
 #pragma unroll
   for (int k = 0; k < A; ++k) integrate_agent<T>(px[k], py[k], vx[k], vy[k], fx[k], fy[k], s.max_speed);
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < A; ++k) st4(s.pv + ((int64_t)(q * A + k) * s.B + b) * 4, Vec4<T>{px[k], py[k], vx[k], vy[k]});
-  }
+}
 
-  // ---- reward: nearest agent of the lane's own landmarks, collisions of the lane's own agents ----
+// reward: nearest agent of the lane's own landmarks, collisions of the lane's own agents; r[k] per own agent,
+// occ / md (benchmark_data) identical on every lane of the env
+template <typename T, int N, int G>
+__device__ __forceinline__ void grp_reward(const EnvState<T> &s, int base_lane, const T (&px)[N / G], const T (&py)[N / G],
+                                           const T (&lx)[N / G], const T (&ly)[N / G], T (&r)[N / G], int (&coll)[N / G],
+                                           int &occ, T &md) {
+  constexpr int A = N / G, L = N;
+  const unsigned FULL = 0xffffffffu;
   T m2[A];
-  int coll[A];
 #pragma unroll
   for (int k = 0; k < A; ++k) coll[k] = 0;
 #pragma unroll
@@ -254,8 +257,9 @@ __global__ void __launch_bounds__(kStepThreads)
   T m[A];
 #pragma unroll
   for (int k = 0; k < A; ++k) m[k] = sqrt(m2[k]);
-  T base = (T)0, md = (T)0;
-  int occ = 0;
+  T base = (T)0;
+  md = (T)0;
+  occ = 0;
 #pragma unroll
   for (int l = 0; l < L; ++l) {  // landmark order, like upstream's loop
     const T ml = __shfl_sync(FULL, m[l % A], base_lane + l / A);
@@ -264,20 +268,77 @@ __global__ void __launch_bounds__(kStepThreads)
     md += ml;
     occ += (ml2 < s.t2_occ) ? 1 : 0;
   }
-  T r[A];
 #pragma unroll
   for (int k = 0; k < A; ++k) {
     T rr = base;
     for (int c = 0; c < coll[k]; ++c) rr -= (T)1;
     r[k] = rr;
   }
-  if (s.track) {  // team return = sum over the lanes of the env, added in lane order (convergent shuffles)
-    T sum = (T)0;
+}
+
+// team reward = sum over the lanes of the env, added in lane order (convergent shuffles); same value on every lane
+template <typename T, int N, int G>
+__device__ __forceinline__ T grp_team_sum(const T (&r)[N / G], int base_lane) {
+  constexpr int A = N / G;
+  T sum = (T)0;
 #pragma unroll
-    for (int k = 0; k < A; ++k) sum += r[k];
-    T tot = (T)0;
+  for (int k = 0; k < A; ++k) sum += r[k];
+  T tot = (T)0;
 #pragma unroll
-    for (int g = 0; g < G; ++g) tot += __shfl_sync(FULL, sum, base_lane + g);
+  for (int g = 0; g < G; ++g) tot += __shfl_sync(0xffffffffu, sum, base_lane + g);
+  return tot;
+}
+
+// Scenario.reset_world for the lane's entities of env b, episode ep (same draws as Env::reset: agents, then landmarks)
+template <typename T, int N, int G>
+__device__ __forceinline__ void grp_reset_draw(const EnvState<T> &s, int64_t b, uint32_t ep, int q, T (&px)[N / G],
+                                               T (&py)[N / G], T (&vx)[N / G], T (&vy)[N / G], T (&lx)[N / G], T (&ly)[N / G]) {
+  constexpr int A = N / G;
+  const uint64_t gid = (uint64_t)(s.gid0 + b);
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    const int ia = q * A + k, il = N + q * A + k;  // entity indices of the lane's k-th agent / landmark
+    const uint4 ra = philox_raw(s.seed, gid, ep, kDomainReset, ia >> 1);
+    px[k] = bits_to_pos<T>((ia & 1) ? ra.z : ra.x); py[k] = bits_to_pos<T>((ia & 1) ? ra.w : ra.y);
+    const uint4 rl = philox_raw(s.seed, gid, ep, kDomainReset, il >> 1);
+    lx[k] = bits_to_pos<T>((il & 1) ? rl.z : rl.x); ly[k] = bits_to_pos<T>((il & 1) ? rl.w : rl.y);
+    vx[k] = vy[k] = (T)0;
+    st4(s.pv + ((int64_t)ia * s.B + b) * 4, Vec4<T>{px[k], py[k], (T)0, (T)0});
+    st2(s.lm + ((int64_t)(q * A + k) * s.B + b) * 2, Vec2<T>{lx[k], ly[k]});
+  }
+}
+
+template <typename T, int N, int G>
+__global__ void __launch_bounds__(kGroupStepThreads)
+    k_step_grp(EnvState<T> s, const int32_t *__restrict__ act_u, T *__restrict__ obs, T *__restrict__ rew,
+               uint8_t *__restrict__ done, int32_t *__restrict__ info_i, T *__restrict__ info_f) {
+  using GL = GroupLayout<T, N, G>;
+  constexpr int A = GL::A, EPW = GL::EPW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int el = lane / G, q = lane - el * G;            // env within the warp, lane within the env
+  const int base_lane = el * G;
+  const int64_t b0 = ((int64_t)blockIdx.x * (kGroupStepThreads / 32) + warp) * EPW;
+  const int64_t b = b0 + el;
+  const bool lane_ok = lane < GL::LANES;
+  const bool active = lane_ok && b < s.B;
+  const bool full = b0 + EPW <= s.B;
+
+  T px[A], py[A], vx[A], vy[A], lx[A], ly[A];
+  int au[A];
+  grp_load<T, N, G>(s, b, q, active, px, py, vx, vy, lx, ly);
+#pragma unroll
+  for (int k = 0; k < A; ++k) au[k] = active ? act_u[b * N + q * A + k] : 0;
+  grp_physics<T, N, G>(s, au, q, base_lane, px, py, vx, vy);
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < A; ++k) st4(s.pv + ((int64_t)(q * A + k) * s.B + b) * 4, Vec4<T>{px[k], py[k], vx[k], vy[k]});
+  }
+  T r[A], md;
+  int coll[A], occ;
+  grp_reward<T, N, G>(s, base_lane, px, py, lx, ly, r, coll, occ, md);
+  if (s.track) {
+    const T tot = grp_team_sum<T, N, G>(r, base_lane);
     if (active && q == 0) { s.ep_ret[b] += tot; s.tstep[b] += 1; }
   }
   if (active) {
@@ -301,7 +362,7 @@ __global__ void __launch_bounds__(kStepThreads)
 // env.reset() / scenario.observation for the same lane layout: Philox reset of the masked (or timed-out) envs, then
 // the observation rows of every env.  Same draws as Env::reset (entities in upstream's order: agents, landmarks).
 template <typename T, int N, int G>
-__global__ void __launch_bounds__(kStepThreads)
+__global__ void __launch_bounds__(kGroupStepThreads)
     k_reset_grp(EnvState<T> s, const uint8_t *__restrict__ mask, T *__restrict__ obs, int auto_len, int do_reset) {
   using GL = GroupLayout<T, N, G>;
   constexpr int A = GL::A, EPW = GL::EPW;
@@ -309,7 +370,7 @@ __global__ void __launch_bounds__(kStepThreads)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int el = lane / G, q = lane - el * G;
   const int base_lane = el * G;
-  const int64_t b0 = ((int64_t)blockIdx.x * (kStepThreads / 32) + warp) * EPW;
+  const int64_t b0 = ((int64_t)blockIdx.x * (kGroupStepThreads / 32) + warp) * EPW;
   const int64_t b = b0 + el;
   const bool lane_ok = lane < GL::LANES;
   const bool active = lane_ok && b < s.B;
@@ -330,17 +391,7 @@ __global__ void __launch_bounds__(kStepThreads)
   if (active) {
     if (doit) {
       const uint32_t ep = ep_old + 1u;
-      const uint64_t gid = (uint64_t)(s.gid0 + b);
-#pragma unroll
-      for (int k = 0; k < A; ++k) {
-        const int ia = q * A + k, il = N + q * A + k;  // entity indices of the lane's k-th agent / landmark
-        const uint4 ra = philox_raw(s.seed, gid, ep, kDomainReset, ia >> 1);
-        px[k] = bits_to_pos<T>((ia & 1) ? ra.z : ra.x); py[k] = bits_to_pos<T>((ia & 1) ? ra.w : ra.y);
-        const uint4 rl = philox_raw(s.seed, gid, ep, kDomainReset, il >> 1);
-        lx[k] = bits_to_pos<T>((il & 1) ? rl.z : rl.x); ly[k] = bits_to_pos<T>((il & 1) ? rl.w : rl.y);
-        st4(s.pv + ((int64_t)ia * s.B + b) * 4, Vec4<T>{px[k], py[k], (T)0, (T)0});
-        st2(s.lm + ((int64_t)(q * A + k) * s.B + b) * 2, Vec2<T>{lx[k], ly[k]});
-      }
+      grp_reset_draw<T, N, G>(s, b, ep, q, px, py, vx, vy, lx, ly);
       if (q == 0) {
         if (s.track && t_old > 0) { ret = (double)s.ep_ret[b]; n_ep = 1.0; n_steps = (double)t_old; }
         s.episode[b] = ep;

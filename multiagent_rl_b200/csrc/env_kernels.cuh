@@ -11,8 +11,11 @@
 #include "env_launch.h"
 
 namespace mpe {
-
 constexpr int kStepThreads = 128;
+}
+
+namespace mpe {
+
 constexpr int kStageMaxBytes = 16384;  // per-warp obs staging above this falls back to per-agent staging
 
 template <typename T, int SC, int N>
@@ -317,13 +320,6 @@ inline EnvState<T> typed(const EnvStateAny &a) {
   s.track = a.track;
   set_thresholds<T>(s, a.scenario);
   return s;
-}
-
-// Team size -> kernel family.  Up to 5 agents: one thread per env (every entity in registers).  6 and more: G lanes
-// per env (env_group.cuh), each owning N / G agents and landmarks; G is the divisor of N that keeps a lane at <= 3
-// agents with the most envs per warp (primes get one agent per lane).
-__host__ __device__ constexpr int group_lanes(int N) {
-  return N <= 5 ? 0 : N == 6 ? 2 : N == 7 ? 7 : N == 8 ? 4 : N == 9 ? 3 : N == 10 ? 5 : N == 11 ? 11 : N == 12 ? 4 : -1;
 }
 
 #define MPE_DISPATCH(a, CALL)                                                       \

@@ -27,6 +27,7 @@
 
 #include "actor_launch.h"
 #include "env_core.cuh"
+#include "env_group.cuh"
 #include "tc_common.cuh"
 
 namespace mpe {
@@ -747,7 +748,7 @@ __host__ __device__ inline size_t tc2_tile_bytes(int N, int Kx, int APAD) {
   // larger teams and the two-head simple_reference actor keep the dense2 shares in the global scratch instead
   return tc_x_bytes(N, Kx) + 16384 + (size_t)((kRows * N * 2 + 127) / 128 * 128) + (N <= 3 && APAD <= 8 ? (size_t)N * APAD * kRows * 4 : 0);
 }
-enum { B2_XR = 0, B2_XF = 4, B2_EXTRA = 8 };  // per tile: operand ring buffer q (< 4) ready / free again
+enum { B2_XR = 0, B2_XF = 4, B2_OBS = 8, B2_EXTRA = 9 };  // per tile: operand ring buffer q (< 4) ready / free again; fused large teams: next observations written
 __host__ __device__ inline size_t tc2_smem_bytes(uint32_t wbytes, int N, int Kx, int APAD) {
   return (size_t)wbytes + 2 * tc2_tile_bytes(N, Kx, APAD) + (1 + 2 * B_PER_WG + 2 * B2_EXTRA) * 8 + 64;
 }
@@ -770,7 +771,9 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
   // two-head actors of small teams (simple_reference, A = 5 + 10): the exchange buffer does not fit into shared memory
   // any more, so the OTHER warpgroup's shares travel through the scratch rows as well (the own shares stay in registers)
   constexpr bool kXs = !kJit && APAD > 8;
-  static_assert(!(kJit && FUSED), "the fused World.step keeps every agent of a row in registers: teams of <= 3");
+  // fused rollout of large teams: the env step runs after the sampling with G lanes per env (env_group.cuh), the
+  // observations of the next step go through an L2-resident work buffer that the operand warp streams back in
+  static_assert(!(kJit && FUSED) || (SC == kSpread && group_lanes(N) > 0), "fused large-team rollout: simple_spread, 6..12 agents");
   extern __shared__ __align__(128) unsigned char smem[];
 #ifdef MPE_TC_PHASES
   if (dbg && threadIdx.x == 0 && blockIdx.x < 148) {
@@ -806,6 +809,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
         mbar_init(&xbars[g * B2_EXTRA + B2_XR + q], 32);  // the service warp filled operand buffer q
         mbar_init(&xbars[g * B2_EXTRA + B2_XF + q], 1);   // the dense1 GEMM reading buffer q has completed
       }
+      mbar_init(&xbars[g * B2_EXTRA + B2_OBS], 128);      // the owner warpgroup wrote the tile's next observations
     }
     mbar_fence_init();
     mbar_expect_tx(&bars[0], w.bytes);
@@ -839,57 +843,66 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
     const int X = warp - 10, lane = tid & 31;
     unsigned char *sm_x = tile_smem(X);
     uint64_t *xb2 = xbars + X * B2_EXTRA;
-    uint32_t ph_xf = 0, filled = 0;  // bit q: phase parity of / first fill done for ring buffer q
-    const bool vec2 = (reinterpret_cast<uintptr_t>(io.obs) & 7) == 0 && (D & 1) == 0;
+    uint32_t ph_xf = 0, filled = 0, ph_obs = 0;  // bit q: phase parity of / first fill done for ring buffer q
+    const float *obs_src = FUSED ? ro.obs_work : io.obs;
+    const int64_t nbx = FUSED ? s.B : io.B;
+    const bool vec2 = (reinterpret_cast<uintptr_t>(obs_src) & 7) == 0 && (D & 1) == 0;
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int64_t tile = pair * 2 + X, env0 = tile * kRows;
-      const int valid = tile < ntiles ? (int)((io.B - env0) < kRows ? (io.B - env0) : kRows) : 0;
+      const int valid = tile < ntiles ? (int)((nbx - env0) < kRows ? (nbx - env0) : kRows) : 0;
 #pragma unroll 1
-      for (int j = 0; j < 2 * N; ++j) {
-        if (!need_e1(j)) continue;
-        const int t = agent_of(j), q = d1_index(j) & (kRing - 1);
-        if ((filled >> q) & 1u) { mbar_wait(&xb2[B2_XF + q], (ph_xf >> q) & 1u); ph_xf ^= 1u << q; }
-        filled |= 1u << q;
-        unsigned char *xh = sm_x + (size_t)(q * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
-#pragma unroll 1
-        for (int rp = 0; rp < 2; ++rp) {  // two rows per round: 2 x 32 values in registers, loads of both in flight
-          float xr[2][32];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int r = lane + 32 * (2 * rp + u);
-#pragma unroll
-            for (int k = 0; k < 32; ++k) xr[u][k] = 0.0f;
-            if (r < valid) {
-              const float *src = io.obs + (env0 + r) * R + t * D;
-              if (vec2) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                  if (2 * k < D) {
-                    const float2 v = *reinterpret_cast<const float2 *>(src + 2 * k);
-                    xr[u][2 * k] = v.x; xr[u][2 * k + 1] = v.y;
-                  }
-              } else {
-#pragma unroll
-                for (int k = 0; k < 32; ++k)
-                  if (k < D) xr[u][k] = src[k];
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int r = lane + 32 * (2 * rp + u);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              if (c * 8 < Kx) {
-                const float v[8] = {xr[u][c * 8], xr[u][c * 8 + 1], xr[u][c * 8 + 2], xr[u][c * 8 + 3],
-                                    xr[u][c * 8 + 4], xr[u][c * 8 + 5], xr[u][c * 8 + 6], xr[u][c * 8 + 7]};
-                store_chunk_split(xh + c * kChunkA, xl + c * kChunkA, r, v);
-              }
-            }
-          }
+      for (int it = 0; it < T; ++it) {
+        if (FUSED && it > 0) {  // the env phase of step it - 1 has written this tile's observations (release / acquire)
+          mbar_wait(&xb2[B2_OBS], ph_obs);
+          ph_obs ^= 1;
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&xb2[B2_XR + q]);
+#pragma unroll 1
+        for (int j = 0; j < 2 * N; ++j) {
+          if (!need_e1(j)) continue;
+          const int t = agent_of(j), q = d1_index(j) & (kRing - 1);
+          if ((filled >> q) & 1u) { mbar_wait(&xb2[B2_XF + q], (ph_xf >> q) & 1u); ph_xf ^= 1u << q; }
+          filled |= 1u << q;
+          unsigned char *xh = sm_x + (size_t)(q * 2) * (Kx / 8) * kChunkA, *xl = xh + (size_t)(Kx / 8) * kChunkA;
+#pragma unroll 1
+          for (int rp = 0; rp < 2; ++rp) {  // two rows per round: 2 x 32 values in registers, loads of both in flight
+            float xr[2][32];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int r = lane + 32 * (2 * rp + u);
+#pragma unroll
+              for (int k = 0; k < 32; ++k) xr[u][k] = 0.0f;
+              if (r < valid) {
+                const float *src = obs_src + (env0 + r) * R + t * D;
+                if (vec2) {
+#pragma unroll
+                  for (int k = 0; k < 16; ++k)
+                    if (2 * k < D) {
+                      const float2 v = *reinterpret_cast<const float2 *>(src + 2 * k);
+                      xr[u][2 * k] = v.x; xr[u][2 * k + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 32; ++k)
+                    if (k < D) xr[u][k] = src[k];
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int r = lane + 32 * (2 * rp + u);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                if (c * 8 < Kx) {
+                  const float v[8] = {xr[u][c * 8], xr[u][c * 8 + 1], xr[u][c * 8 + 2], xr[u][c * 8 + 3],
+                                      xr[u][c * 8 + 4], xr[u][c * 8 + 5], xr[u][c * 8 + 6], xr[u][c * 8 + 7]};
+                  store_chunk_split(xh + c * kChunkA, xl + c * kChunkA, r, v);
+                }
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&xb2[B2_XR + q]);
+        }
       }
     }
   } else if (warp >= 8) {
@@ -1175,6 +1188,8 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
           // groups of G agents: logits = bias + the four scratch shares (two warpgroups x two directions); the G * 2
           // Philox blocks and the G * 5 Gumbel transforms of a group run in lock-step
           constexpr int G = (N % 3 == 0) ? 3 : 2, NQ = APAD / 4;
+          const uint64_t jstep = FUSED ? ro.step0 + (uint64_t)it : io.step, jseed = FUSED ? s.seed : io.seed;
+          const int64_t jgid0 = FUSED ? s.gid0 : io.gid0;
 #pragma unroll 1
           for (int t0 = 0; t0 < N; t0 += G) {
             float lgt[G][APAD], gn[G][APAD];
@@ -1191,7 +1206,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
 #pragma unroll
               for (int a = 0; a < APAD; ++a) gn[u][a] = 0.0f;
             }
-            if (io.gumbel != nullptr) {
+            if (!FUSED && io.gumbel != nullptr) {
               if (mine) {
 #pragma unroll
                 for (int u = 0; u < G; ++u)
@@ -1205,8 +1220,8 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
               for (int u = 0; u < G; ++u)
 #pragma unroll
                 for (int jj = 0; jj < NQ; ++jj)
-                  c[u * NQ + jj] = philox_counter((uint64_t)(io.gid0 + b), (uint32_t)io.step, kDomainGumbel, (t0 + u) * 8 + jj);
-              philox4x32_10_batch<G * NQ>(c, philox_key(io.seed));
+                  c[u * NQ + jj] = philox_counter((uint64_t)(jgid0 + b), (uint32_t)jstep, kDomainGumbel, (t0 + u) * 8 + jj);
+              philox4x32_10_batch<G * NQ>(c, philox_key(jseed));
               if (w.A == 5) {
                 uint32_t r[G * 5];
                 float g[G * 5];
@@ -1256,7 +1271,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
               }
               own_act[(row * N + t) * 2] = (uint8_t)bu;
               own_act[(row * N + t) * 2 + 1] = (uint8_t)bc;
-              if (mine && io.logits != nullptr) {
+              if (!FUSED && mine && io.logits != nullptr) {
 #pragma unroll
                 for (int a = 0; a < APAD; ++a)
                   if (a < w.A) io.logits[(b * N + t) * w.A + a] = lgt[u][a];
@@ -1364,7 +1379,67 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
         }
 
         TL(half, 29);
-        if (FUSED) {
+        if constexpr (FUSED && kJit) {
+          // ---- own tile, large teams: World.step + reward + outputs with G lanes per env (env_group.cuh) ----
+          // A warp of the owner warpgroup holds rows 32w .. 32w + 31 of the tile and walks them EPW envs at a time.
+          constexpr int G = group_lanes(N), A = N / G, EPW = 32 / G, PASSES = (32 + EPW - 1) / EPW;
+          const unsigned FULL = 0xffffffffu;
+          const int lane = row & 31, wq = row >> 5;
+          const int el = lane / G, q = lane - el * G, base_lane = el * G;
+          const bool lane_ok = lane < EPW * G;
+          const int64_t toff = (int64_t)it * s.B;
+          float *g_obs = ro.obs_next != nullptr ? ro.obs_next + toff * R : nullptr;
+          float *g_rew = ro.rew != nullptr ? ro.rew + toff * N : nullptr;
+          bar_sync_n(2 + own, 128);  // the tile's sampled actions are in own_act
+#pragma unroll 1
+          for (int p = 0; p < PASSES; ++p) {
+            const int e_in_warp = p * EPW + el, rloc = wq * 32 + e_in_warp;
+            const bool active = lane_ok && e_in_warp < 32 && rloc < valid;
+            const int64_t bb = env0 + rloc;
+            float px[A], py[A], vx[A], vy[A], lx[A], ly[A];
+            int au[A];
+            grp_load<float, N, G>(s, bb, q, active, px, py, vx, vy, lx, ly);
+#pragma unroll
+            for (int k = 0; k < A; ++k) au[k] = active ? (int)own_act[(rloc * N + q * A + k) * 2] : 0;
+            grp_physics<float, N, G>(s, au, q, base_lane, px, py, vx, vy);
+            float r[A], md;
+            int coll[A], occ;
+            grp_reward<float, N, G>(s, base_lane, px, py, lx, ly, r, coll, occ, md);
+            const float tot = grp_team_sum<float, N, G>(r, base_lane);
+            // episode bookkeeping lives with the env's first lane; its lanes learn whether the episode ends
+            int ts = 0;
+            uint32_t ep_old = 0;
+            float epr = 0.0f;
+            if (active && q == 0) { epr = s.ep_ret[bb] + tot; ts = s.tstep[bb] + 1; ep_old = s.episode[bb]; }
+            ts = __shfl_sync(FULL, ts, base_lane);
+            ep_old = __shfl_sync(FULL, ep_old, base_lane);
+            const bool do_reset = active && max_episode_len > 0 && ts >= max_episode_len;
+            GroupLanes<float, N, G> gl{0, lane, el, q, base_lane, bb - el, bb, lane_ok, active, false};
+            if (g_obs != nullptr || g_rew != nullptr)  // the step's recorded outputs (before a reset)
+              grp_emit<float, N, G>(gl, px, py, vx, vy, lx, ly, r, g_obs, g_rew, nullptr);
+            double ret = 0.0, n_ep = 0.0, n_steps = 0.0;
+            if (do_reset) {  // experiments/run.py:59-60
+              grp_reset_draw<float, N, G>(s, bb, ep_old + 1u, q, px, py, vx, vy, lx, ly);
+              if (q == 0) {
+                ret = (double)epr; n_ep = 1.0; n_steps = (double)ts;
+                s.episode[bb] = ep_old + 1u; s.tstep[bb] = 0; s.ep_ret[bb] = 0.0f;
+              }
+            } else if (active) {
+#pragma unroll
+              for (int k = 0; k < A; ++k) st4(s.pv + ((int64_t)(q * A + k) * s.B + bb) * 4, Vec4<float>{px[k], py[k], vx[k], vy[k]});
+              if (q == 0) { s.ep_ret[bb] = epr; s.tstep[bb] = ts; }
+            }
+            fold_stats(s.stats, ret, n_ep, n_steps);
+            // what the actor sees next: the observation of the (possibly fresh) state, via the L2-resident work buffer
+            if (it + 1 < T) grp_emit<float, N, G>(gl, px, py, vx, vy, lx, ly, nullptr, ro.obs_work, nullptr, nullptr);
+          }
+          if (ro.act_u != nullptr)
+            for (int i = row; i < valid * N; i += 128) ro.act_u[(toff + env0) * N + i] = own_act[i * 2];
+          if (it + 1 < T) {
+            __threadfence();
+            mbar_arrive(&xbars[own * B2_EXTRA + B2_OBS]);
+          }
+        } else if constexpr (FUSED) {
           // ---- own tile: World.step + reward + outputs for env row `row` ----
           const int64_t toff = (int64_t)it * s.B;
           bool do_reset = false;
@@ -1559,7 +1634,11 @@ bool tc_actor_supported(const TcDev &w, int N) {
   // teams of > 3 agents keep one head of <= 8 entries (launch_actor_forward_tc); wider heads go to the FFMA kernel
   return tc_supported(w) && (N == 2 || N == 3 || ((N == 4 || N == 6 || N == 9 || N == 12) && w.A <= 8 && w.scratch != nullptr));
 }
-bool tc_rollout_supported(const TcDev &w, int N) { return tc_supported(w) && (N == 2 || N == 3); }
+bool tc_rollout_supported(const TcDev &w, int N) {
+  // one kernel for all T steps: teams of <= 3 (every agent of an env in one thread's registers) and the large
+  // simple_spread teams with a tensor-core actor instantiation (env step with G lanes per env)
+  return tc_supported(w) && (N == 2 || N == 3 || ((N == 6 || N == 9 || N == 12) && w.A <= 8 && w.scratch != nullptr));
+}
 size_t tc_scratch_floats(int sm_count) {
   // the largest of: k_tc's forward shares; k_tc2's per-cell shares for the instantiated large teams (N <= 12, one head
   // of <= 8 entries) and for the two-head small teams (N <= 3, 16 entries)
@@ -1601,6 +1680,10 @@ cudaError_t launch_rollout_tc(const EnvStateAny &a, const TcDev &w, const Rollou
   if (a.scenario == kSpeaker) return launch_tc_t<kSpeaker, 2, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
   if (a.N == 2) return launch_tc_t<kSpread, 2, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
   if (a.N == 3) return launch_tc_t<kSpread, 3, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
+  if (ro.obs_work == nullptr) return cudaErrorInvalidValue;  // large teams need the observation work buffer
+  if (a.N == 6) return launch_tc_t<kSpread, 6, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
+  if (a.N == 9) return launch_tc_t<kSpread, 9, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
+  if (a.N == 12) return launch_tc_t<kSpread, 12, true, 8>(s, w, io, ro, a.max_episode_len, a.B, st);
   return cudaErrorInvalidValue;
 }
 

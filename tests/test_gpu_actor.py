@@ -135,10 +135,10 @@ def test_get_exploration_action_surface(golden_dir):
     assert a[0].shape == (64, 2, 5)
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_fused_large'])
 @pytest.mark.parametrize('scenario,n,B', [('simple_spread', None, 10_000 + 13), ('simple_spread', 6, 2000),
-                                          ('simple_spread', 12, 500), ('simple_reference', None, 3000),
-                                          ('simple_speaker_listener', None, 3000)])
+                                          ('simple_spread', 9, 1000), ('simple_spread', 12, 500),
+                                          ('simple_reference', None, 3000), ('simple_speaker_listener', None, 3000)])
 def test_fused_rollout_equals_stepwise_path(scenario, n, B, impl):
     """mpe_rollout (one kernel, T steps, in-kernel auto-reset) == actor_forward + mpe_step + mpe_reset
     called step by step with the same Philox keys: actions bit-exact, values bit-exact."""
@@ -150,7 +150,7 @@ def test_fused_rollout_equals_stepwise_path(scenario, n, B, impl):
     for k in sd:
         if 'dense2' in k:
             sd[k] = sd[k] * 3.0
-    if impl not in _impls(spec.N):
+    if impl.replace('_fused_large', '') not in _impls(spec.N) or (impl == 'tc_fused_large' and spec.N <= 3):
         pytest.skip('not covered by the tensor-core path')
     actor = m.FusedActor(sd, seed=seed, impl=impl)
     fused = m.make_env(scenario, n=n, num_envs=B, batched=True, seed=seed, max_episode_len=L)
@@ -191,7 +191,7 @@ def test_fused_rollout_vs_float64_oracle_directly(scenario, n, B):
     A = [5, 10] if scenario == 'simple_reference' else 5
     sd = actor_ref.init_state_dict(spec.obs_dim, A, 17)
     env = m.make_env(scenario, n=n, num_envs=B, batched=True, seed=seed, max_episode_len=T)
-    actor = m.FusedActor(sd, seed=seed)
+    actor = m.FusedActor(sd, seed=seed, impl='tc_fused_large' if spec.N > 3 else 'auto')  # the single-kernel form everywhere
     obs0 = env.reset()
     pos, vel, lm, goal = env.get_state()
     v = mpe_vec.VecEnv(spec, B)
@@ -341,9 +341,10 @@ def test_fused_rollout_full_size_properties(B):
     assert float((act_u[0] != act_u[1]).float().mean()) > 0.2
 
 
+@pytest.mark.parametrize('impl', ['auto', 'tc_fused_large'])
 @pytest.mark.parametrize('scenario,n,A', [('simple_spread', None, 5), ('simple_reference', None, [5, 10]),
                                           ('simple_speaker_listener', None, 5), ('simple_spread', 6, 5)])
-def test_fused_rollout_equals_stepwise_path_tiny_batches(scenario, n, A):
+def test_fused_rollout_equals_stepwise_path_tiny_batches(scenario, n, A, impl):
     """Batches of 1, 2 and 129 envs (one row of one tile, a tile pair whose second tile has one row): the rollout
     (one kernel for small teams, actor + step kernels for large ones) equals the step-by-step calls bit for bit,
     across auto-resets."""
@@ -351,7 +352,7 @@ def test_fused_rollout_equals_stepwise_path_tiny_batches(scenario, n, A):
     for B in (1, 2, 129):
         env = m.make_env(scenario, n=n, num_envs=B, batched=True, seed=3, max_episode_len=4)
         env2 = m.make_env(scenario, n=n, num_envs=B, batched=True, seed=3, max_episode_len=4)
-        actor = m.FusedActor(actor_ref.init_state_dict(env.obs_dim, A, 1), seed=3)  # the rollout draws with the env's seed
+        actor = m.FusedActor(actor_ref.init_state_dict(env.obs_dim, A, 1), seed=3, impl=impl)  # the rollout draws with the env's seed
         env.reset()
         obs = env2.reset()
         rec = env.rollout(actor, 9, step0=0, record=True)

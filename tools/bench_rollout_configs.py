@@ -13,10 +13,11 @@ CONFIGS = [('simple_spread', None, 65536), ('simple_spread', 6, 65536), ('simple
            ('simple_spread', 12, 32768), ('simple_reference', None, 65536), ('simple_speaker_listener', None, 65536)]
 # the same at 1,048,576 envs per GPU (no tail quantisation: thousands of tile pairs per SM)
 CONFIGS += [(s, n, 1 << 20) for s, n, _ in CONFIGS]
+IMPL = sys.argv[1] if len(sys.argv) > 1 else 'auto'  # 'tc_fused_large': teams of 6 / 9 / 12 as one kernel per call
 for scen, n, B in CONFIGS:
     env = m.make_env(scen, n=n, num_envs=B, batched=True, seed=1, max_episode_len=25)
     A = [5, 10] if scen == 'simple_reference' else 5
-    actor = m.FusedActor(random_state_dict(env.obs_dim, A, 1), seed=1)
+    actor = m.FusedActor(random_state_dict(env.obs_dim, A, 1), seed=1, impl=IMPL)
     env.reset()
     T = 25
     env.rollout(actor, T)
@@ -28,6 +29,6 @@ for scen, n, B in CONFIGS:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (4 * T)
-    print(json.dumps({'scenario': scen, 'N': env.n, 'envs': B, 'ms_per_env_step': round(ms, 4),
+    print(json.dumps({'scenario': scen, 'N': env.n, 'envs': B, 'impl': IMPL, 'ms_per_env_step': round(ms, 4),
                       'G_agent_steps_per_s': round(B * env.n / ms / 1e6, 3)}))
     del env, actor
