@@ -329,7 +329,7 @@ def run_b200(args):
     e2e_steps = max(25, min(args.steps, 100))
     del env
     best = None
-    for shards in (3, 4, 2):
+    for shards in (3, 4, 2, 1):  # 1 = one direction at a time: the better schedule when many ranks oversubscribe the host
         hr = m.HostRollout(SCENARIO, B, actor, shards=shards, seed=SEED, env_id_offset=off, device=dev,
                            max_episode_len=EP_LEN)
         seen = [0.0]

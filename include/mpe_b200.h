@@ -121,7 +121,7 @@ int mpe_host_wait(void *stream);
  * as H2D obs_host [B][N][D] -> actor forward + sample (Philox keyed by the env's seed, global env ids and `step`) ->
  * env step on the sampled actions -> ONE D2H of the transition block {act_u, act_c, obs', rew, done} laid out as
  * mpe_host_block_layout says (offsets in bytes, each 256 B aligned; act_u / act_c int32 [B][N], obs' fp32 [B][N][D],
- * rew fp32 [B][N], done uint8 [B][N]).  Compared with actor_forward_host_async + mpe_step_host_async the sampled
+ * rew fp32 [B][N], done uint8 [B][N]; act_c has zero length - off_act_c == off_obs - for envs without a message head).  Compared with actor_forward_host_async + mpe_step_host_async the sampled
  * actions are not bounced through the host before the step reads them and the four downloads are one copy; every
  * step still uploads the observations and downloads everything the two calls return.  Enqueued on `stream`, no host
  * synchronisation (mpe_host_wait).  fp32 envs. */

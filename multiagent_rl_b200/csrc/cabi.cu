@@ -521,7 +521,7 @@ static MpeHostBlockLayout block_layout(const mpe::EnvStateAny &s) {
   MpeHostBlockLayout l;
   l.off_act_u = 0;
   l.off_act_c = up(l.off_act_u + rows * 4);
-  l.off_obs = up(l.off_act_c + rows * 4);
+  l.off_obs = up(l.off_act_c + (s.act_c > 0 ? rows * 4 : 0));  // no message head: act_c has zero length (off_act_c == off_obs)
   l.off_rew = up(l.off_obs + rows * s.D * rs);
   l.off_done = up(l.off_rew + rows * rs);
   l.bytes = up(l.off_done + rows);

@@ -51,4 +51,26 @@ if which in ('all', 'bign'):
         for _ in range(3):
             env.step(act)
         torch.cuda.synchronize()
+    # the opt-in single-kernel rollout of a 6-agent team (T = 2)
+    af = m.FusedActor(random_state_dict(16, 5, 1), device=dev, seed=1, impl='tc_fused_large')
+    env6.rollout(af, 2)
+    torch.cuda.synchronize()
+if which == 'critic':
+    import numpy as np
+    rng = np.random.RandomState(0)
+    D, N, B = 10, 3, 65536
+    csd = {'dense1.module.weight': rng.randn(64, D + 5).astype(np.float32) * 0.1, 'dense1.module.bias': np.zeros(64, np.float32),
+           'lstm.weight_ih_l0': rng.randn(256, 64).astype(np.float32) * 0.1, 'lstm.weight_hh_l0': rng.randn(256, 64).astype(np.float32) * 0.1,
+           'lstm.bias_ih_l0': np.zeros(256, np.float32), 'lstm.bias_hh_l0': np.zeros(256, np.float32),
+           'dense2.weight': rng.randn(1, 64).astype(np.float32), 'dense2.bias': np.zeros(1, np.float32)}
+    critic = m.FusedCritic(csd, obs_dim=D)
+    obs = torch.randn((B, N, D), device=dev)
+    act = torch.eye(5, device=dev)[torch.randint(0, 5, (B, N), device=dev)]
+    for _ in range(3):
+        critic.forward(obs, act)
+    am = m.FusedActor(random_state_dict(16, 5, 1, model_head=True), device=dev, seed=1)
+    o6 = torch.randn((B, 6, 16), device=dev)
+    for _ in range(2):
+        am.forward(o6, want_next_state=True)
+    torch.cuda.synchronize()
 print('profile target done')
