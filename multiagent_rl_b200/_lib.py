@@ -201,7 +201,10 @@ class HostBlock(object):
 
     def free(self):
         if getattr(self, 'ptr', None):
-            load().mpe_host_free(C.c_void_p(self.ptr))
-            self.ptr = None
+            ptr, self.ptr = self.ptr, None
+            try:
+                load().mpe_host_free(C.c_void_p(ptr))
+            except Exception:  # noqa: BLE001 - interpreter shutdown: the library may already be gone
+                pass
 
     __del__ = free

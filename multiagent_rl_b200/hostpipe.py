@@ -121,6 +121,8 @@ class HostRollout(object):
         if getattr(self, '_block', None) is not None:
             try:
                 self.wait()
+            except Exception:  # noqa: BLE001 - interpreter shutdown / a failed stream: still release the memory
+                pass
             finally:
                 self._block.free()
                 self._block = None
