@@ -40,10 +40,12 @@ def use_reference(backend):
     return scen_mod, run_mod, arglist
 
 
-def main_py_setup(env, seed, model=False):
+def main_py_setup(env, seed, model=False, bic=False):
     """main.py:41-61 / main_scalability_1.py:38-58: seeds, dims, networks of the reference's own classes."""
     import torch
-    if model:
+    if bic:  # main.py:15-18, the BiCNet baseline
+        from rls.model.ac_network_multi_gumbel_BIC import ActorNetwork, CriticNetwork
+    elif model:
         from rls.model.ac_network_model_multi_gumbel import ActorNetwork, CriticNetwork
     else:
         from rls.model.ac_network_multi_gumbel import ActorNetwork, CriticNetwork
@@ -82,13 +84,15 @@ def verify_memory(memory, scenario, n, obs_tol=5e-5, rew_tol=2e-4):
     ora = mpe_ref.make_env(scenario, n=n)
     count = 0
     for obs_n, action_n, rew_shared, new_obs_n, done in memory._storage:
-        assert done == 0.0
+        assert np.all(np.asarray(done) == 0.0)   # run.py stores float(done), run_BIC.py a list of floats
         for a in action_n:  # exact one-hots of width 5 (force_discrete_action's in-place rewrite)
             assert a.shape == (5,) and a.sum() == 1.0 and set(np.unique(a)) <= {0.0, 1.0}
         pos, vel, lm = state_from_obs(scenario, obs_n)
         mpe_ref.set_state(ora, pos, vel, lm)
         o, r, _, _ = ora.step([np.array(a, dtype=np.float64) for a in action_n])
         assert np.abs(np.stack(o) - np.stack(new_obs_n)).max() <= obs_tol, count
-        assert abs(np.sum(r) - rew_shared) <= rew_tol * len(r), count
+        assert abs(np.sum(r) - np.sum(rew_shared)) <= rew_tol * len(r), count  # run_BIC.py stores the per-agent list
+        if np.ndim(rew_shared) == 1:
+            assert np.abs(np.asarray(r) - np.asarray(rew_shared)).max() <= rew_tol, count
         count += 1
     return count

@@ -164,3 +164,19 @@ def test_reference_run_on_the_communication_scenarios(ref, scenario):
         assert np.abs(d - d[0]).max() < 1e-5
         if scenario == 'simple_reference':  # the message agent 0 sent is what agent 1 observes next
             assert np.array_equal(o2[1, 11:21], action_n[0][5:15]) and np.array_equal(o2[0, 11:21], action_n[1][5:15])
+
+
+def test_reference_bicnet_baseline_loop(ref):
+    """main.py:15-18: the BiCNet baseline (experiments/run_BIC.py, BIC_gumbel_fix.Trainer, per-agent rewards and dones
+    in the replay tuples) - same actor architecture, so the fused acting path serves it too."""
+    scen, _, arglist = ref
+    import experiments.run_BIC as run_bic
+    from rls.agent.multiagent.BIC_gumbel_fix import Trainer as RefTrainer
+    env = scen.make_env('simple_spread', benchmark=False, discrete_action=True, local_observation=True)
+    actor, critic, action_type = _refloop.main_py_setup(env, 12345678, bic=True)
+    arglist.num_episodes = 2
+    keep = []
+    run_bic.run(env, actor, critic, _trainer_class(RefTrainer, True, keep), 'simple_spread', action_type, cnt=0)
+    mem = keep[0].memory
+    assert len(mem) == 50 and _refloop.verify_memory(mem, 'simple_spread', None) == 50
+    assert len(mem._storage[0][2]) == 3 and mem._storage[0][4] == [0.0, 0.0, 0.0]
