@@ -6,7 +6,7 @@
 // rls/agent/multiagent/ddpg_gumbel_fix.py:151,159,191 (optimize) and model_ddpg_gumbel_fix.py:155,163,199.
 // not on the acting path; here so that imagined rollouts / TD targets can stay on the device.
 //
-// Mapping: one warp per sample.  A persistent CTA (8 warps) keeps the packed weights (W_ih, W_hh: 2 x 64 x 256 fp32 =
+// Mapping: one warp per pair of samples (each weight row read from shared memory serves both).  A persistent CTA (8 warps) keeps the packed weights (W_ih, W_hh: 2 x 64 x 256 fp32 =
 // 128 KB, plus dense1 / heads) in shared memory, loaded once with a TMA bulk copy.  Lane l owns hidden units l and
 // l + 32: its 8 gate pre-activations per step are one 32 B slice of a k-major weight row, x_t / h_{t-1} are broadcast
 // reads of the warp's staging row.  All arithmetic fp32 (FFMA), exp / tanh by the accurate libdevice forms.
@@ -74,12 +74,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// per-warp staging: the input row, x_t = relu(dense1), h_{t-1}, and every step's output for the attention
+constexpr int kCriticR = 2;  // samples per warp and pass: every weight row read from shared memory serves both
+
+// per-warp staging: the input rows, x_t = relu(dense1) and h_{t-1} of the warp's kCriticR samples (every step's output,
+// which the attention needs, stays in the registers of the lane that owns the unit)
 struct CriticWarpSmem {
-  float in[kCriticMaxIn];
-  float x[kCriticH];
-  float h[kCriticH];
-  float out[kCriticMaxAgents][kCriticH];
+  float in[kCriticR][kCriticMaxIn];
+  float x[kCriticR][kCriticH];
+  float h[kCriticR][kCriticH];
 };
 
 __global__ void __launch_bounds__(kCriticThreads, 1)
@@ -102,80 +104,121 @@ __global__ void __launch_bounds__(kCriticThreads, 1)
   const float *Wih = sw + w.off_wih + lane * 8, *Whh = sw + w.off_whh + lane * 8, *bg = sw + w.off_bg + lane * 8;
   const float *W1 = sw + w.off_w1, *b1 = sw + w.off_b1;
   const int D = w.D, A = w.A, Din = w.Din;
-  for (int64_t b = (int64_t)blockIdx.x * kCriticWarps + warp; b < B; b += (int64_t)gridDim.x * kCriticWarps) {
-    float c0 = 0.0f, c1 = 0.0f, h0 = 0.0f, h1 = 0.0f;
-    s.h[lane] = 0.0f; s.h[lane + 32] = 0.0f;
-    for (int t = 0; t < N; ++t) {
-      // obs_act = cat(obs, action) (ac_network_multi_gumbel.py:131-134)
-      __syncwarp();
-      for (int k = lane; k < Din; k += 32)
-        s.in[k] = k < D ? obs[(b * N + t) * D + k] : action[(b * N + t) * A + (k - D)];
-      __syncwarp();
-      // relu(dense1): lane computes outputs lane and lane + 32
-      float a0 = b1[lane], a1 = b1[lane + 32];
-      for (int k = 0; k < Din; ++k) {
-        const float xk = s.in[k];
-        a0 = fmaf(xk, W1[k * kCriticH + lane], a0);
-        a1 = fmaf(xk, W1[k * kCriticH + lane + 32], a1);
-      }
-      s.x[lane] = fmaxf(a0, 0.0f); s.x[lane + 32] = fmaxf(a1, 0.0f);
-      __syncwarp();
-      // gates = b + W_ih x_t + W_hh h_{t-1}; packed columns [i0 i1 f0 f1 g0 g1 o0 o1] of units (lane, lane + 32)
-      float acc[8];
-      {
-        const float4 u = *reinterpret_cast<const float4 *>(bg), v = *reinterpret_cast<const float4 *>(bg + 4);
-        acc[0] = u.x; acc[1] = u.y; acc[2] = u.z; acc[3] = u.w; acc[4] = v.x; acc[5] = v.y; acc[6] = v.z; acc[7] = v.w;
-      }
-#pragma unroll 4
-      for (int k = 0; k < kCriticH; ++k) {
-        const float xk = s.x[k], hk = s.h[k];
-        const float4 u = *reinterpret_cast<const float4 *>(Wih + k * kGates), v = *reinterpret_cast<const float4 *>(Wih + k * kGates + 4);
-        const float4 p = *reinterpret_cast<const float4 *>(Whh + k * kGates), z = *reinterpret_cast<const float4 *>(Whh + k * kGates + 4);
-        acc[0] = fmaf(xk, u.x, acc[0]); acc[1] = fmaf(xk, u.y, acc[1]); acc[2] = fmaf(xk, u.z, acc[2]); acc[3] = fmaf(xk, u.w, acc[3]);
-        acc[4] = fmaf(xk, v.x, acc[4]); acc[5] = fmaf(xk, v.y, acc[5]); acc[6] = fmaf(xk, v.z, acc[6]); acc[7] = fmaf(xk, v.w, acc[7]);
-        acc[0] = fmaf(hk, p.x, acc[0]); acc[1] = fmaf(hk, p.y, acc[1]); acc[2] = fmaf(hk, p.z, acc[2]); acc[3] = fmaf(hk, p.w, acc[3]);
-        acc[4] = fmaf(hk, z.x, acc[4]); acc[5] = fmaf(hk, z.y, acc[5]); acc[6] = fmaf(hk, z.z, acc[6]); acc[7] = fmaf(hk, z.w, acc[7]);
-      }
-      c0 = sigmoid_acc(acc[2]) * c0 + sigmoid_acc(acc[0]) * tanhf(acc[4]);
-      c1 = sigmoid_acc(acc[3]) * c1 + sigmoid_acc(acc[1]) * tanhf(acc[5]);
-      h0 = sigmoid_acc(acc[6]) * tanhf(c0);
-      h1 = sigmoid_acc(acc[7]) * tanhf(c1);
-      __syncwarp();  // every lane has read h_{t-1}
-      s.h[lane] = h0; s.h[lane + 32] = h1;
-      s.out[t][lane] = h0; s.out[t][lane + 32] = h1;
+  const int64_t npass = (B + kCriticR - 1) / kCriticR;
+  for (int64_t pass = (int64_t)blockIdx.x * kCriticWarps + warp; pass < npass; pass += (int64_t)gridDim.x * kCriticWarps) {
+    int64_t bs[kCriticR];
+    bool ok[kCriticR];
+#pragma unroll
+    for (int u = 0; u < kCriticR; ++u) {
+      ok[u] = pass * kCriticR + u < B;
+      bs[u] = ok[u] ? pass * kCriticR + u : pass * kCriticR;  // an odd tail recomputes its first sample, stores nothing
     }
-    __syncwarp();
-    // attention_net (:103-110): scores = <output_t, h_N>, softmax over the agent axis, weighted sum of the outputs
-    float score[kCriticMaxAgents];
-    float mx = -INFINITY;
+    float c0[kCriticR], c1[kCriticR], h0[kCriticR], h1[kCriticR];
+    float o0[kCriticR][kCriticMaxAgents], o1[kCriticR][kCriticMaxAgents];  // outputs of the lane's two units, per step
+#pragma unroll
+    for (int u = 0; u < kCriticR; ++u) {
+      c0[u] = c1[u] = h0[u] = h1[u] = 0.0f;
+      s.h[u][lane] = 0.0f; s.h[u][lane + 32] = 0.0f;
+    }
 #pragma unroll
     for (int t = 0; t < kCriticMaxAgents; ++t) {
       if (t < N) {
-        score[t] = warp_sum(s.out[t][lane] * h0 + s.out[t][lane + 32] * h1);
-        mx = fmaxf(mx, score[t]);
+        // obs_act = cat(obs, action) (ac_network_multi_gumbel.py:131-134)
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < kCriticR; ++u)
+          for (int k = lane; k < Din; k += 32)
+            s.in[u][k] = k < D ? obs[(bs[u] * N + t) * D + k] : action[(bs[u] * N + t) * A + (k - D)];
+        __syncwarp();
+        // relu(dense1): lane computes outputs lane and lane + 32
+        float a0[kCriticR], a1[kCriticR];
+#pragma unroll
+        for (int u = 0; u < kCriticR; ++u) { a0[u] = b1[lane]; a1[u] = b1[lane + 32]; }
+        for (int k = 0; k < Din; ++k) {
+          const float wa = W1[k * kCriticH + lane], wb = W1[k * kCriticH + lane + 32];
+#pragma unroll
+          for (int u = 0; u < kCriticR; ++u) {
+            const float xk = s.in[u][k];
+            a0[u] = fmaf(xk, wa, a0[u]);
+            a1[u] = fmaf(xk, wb, a1[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kCriticR; ++u) { s.x[u][lane] = fmaxf(a0[u], 0.0f); s.x[u][lane + 32] = fmaxf(a1[u], 0.0f); }
+        __syncwarp();
+        // gates = b + W_ih x_t + W_hh h_{t-1}; packed columns [i0 i1 f0 f1 g0 g1 o0 o1] of units (lane, lane + 32)
+        float acc[kCriticR][8];
+        {
+          const float4 bu = *reinterpret_cast<const float4 *>(bg), bv = *reinterpret_cast<const float4 *>(bg + 4);
+#pragma unroll
+          for (int u = 0; u < kCriticR; ++u) {
+            acc[u][0] = bu.x; acc[u][1] = bu.y; acc[u][2] = bu.z; acc[u][3] = bu.w;
+            acc[u][4] = bv.x; acc[u][5] = bv.y; acc[u][6] = bv.z; acc[u][7] = bv.w;
+          }
+        }
+#pragma unroll 2
+        for (int k = 0; k < kCriticH; ++k) {
+          const float4 iu = *reinterpret_cast<const float4 *>(Wih + k * kGates), iv = *reinterpret_cast<const float4 *>(Wih + k * kGates + 4);
+          const float4 hu = *reinterpret_cast<const float4 *>(Whh + k * kGates), hv = *reinterpret_cast<const float4 *>(Whh + k * kGates + 4);
+#pragma unroll
+          for (int u = 0; u < kCriticR; ++u) {
+            const float xk = s.x[u][k], hk = s.h[u][k];
+            acc[u][0] = fmaf(xk, iu.x, acc[u][0]); acc[u][1] = fmaf(xk, iu.y, acc[u][1]);
+            acc[u][2] = fmaf(xk, iu.z, acc[u][2]); acc[u][3] = fmaf(xk, iu.w, acc[u][3]);
+            acc[u][4] = fmaf(xk, iv.x, acc[u][4]); acc[u][5] = fmaf(xk, iv.y, acc[u][5]);
+            acc[u][6] = fmaf(xk, iv.z, acc[u][6]); acc[u][7] = fmaf(xk, iv.w, acc[u][7]);
+            acc[u][0] = fmaf(hk, hu.x, acc[u][0]); acc[u][1] = fmaf(hk, hu.y, acc[u][1]);
+            acc[u][2] = fmaf(hk, hu.z, acc[u][2]); acc[u][3] = fmaf(hk, hu.w, acc[u][3]);
+            acc[u][4] = fmaf(hk, hv.x, acc[u][4]); acc[u][5] = fmaf(hk, hv.y, acc[u][5]);
+            acc[u][6] = fmaf(hk, hv.z, acc[u][6]); acc[u][7] = fmaf(hk, hv.w, acc[u][7]);
+          }
+        }
+        __syncwarp();  // every lane has read h_{t-1}
+#pragma unroll
+        for (int u = 0; u < kCriticR; ++u) {
+          c0[u] = sigmoid_acc(acc[u][2]) * c0[u] + sigmoid_acc(acc[u][0]) * tanhf(acc[u][4]);
+          c1[u] = sigmoid_acc(acc[u][3]) * c1[u] + sigmoid_acc(acc[u][1]) * tanhf(acc[u][5]);
+          h0[u] = sigmoid_acc(acc[u][6]) * tanhf(c0[u]);
+          h1[u] = sigmoid_acc(acc[u][7]) * tanhf(c1[u]);
+          s.h[u][lane] = h0[u]; s.h[u][lane + 32] = h1[u];
+          o0[u][t] = h0[u]; o1[u][t] = h1[u];
+        }
       }
     }
-    float den = 0.0f;
+    __syncwarp();
+    // attention_net (:103-110): scores = <output_t, h_N>, softmax over the agent axis, weighted sum of the outputs
 #pragma unroll
-    for (int t = 0; t < kCriticMaxAgents; ++t)
-      if (t < N) { score[t] = expf(score[t] - mx); den += score[t]; }
-    float n0 = 0.0f, n1 = 0.0f;
+    for (int u = 0; u < kCriticR; ++u) {
+      float score[kCriticMaxAgents];
+      float mx = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < kCriticMaxAgents; ++t)
-      if (t < N) {
-        const float a = score[t] / den;
-        n0 = fmaf(s.out[t][lane], a, n0);
-        n1 = fmaf(s.out[t][lane + 32], a, n1);
-      }
-    if (w.relu_attn) { n0 = fmaxf(n0, 0.0f); n1 = fmaxf(n1, 0.0f); }  // ac_network_multi_gumbel.py:141 only
-    for (int o = 0; o < w.out; ++o) {
-      const float *W2 = sw + w.off_w2;
-      const float v = warp_sum(n0 * W2[lane * kCriticMaxOut + o] + n1 * W2[(lane + 32) * kCriticMaxOut + o]);
-      if (lane == 0) q[b * w.out + o] = v + sw[w.off_b2 + o];
-      if (w.has_r && r != nullptr) {
-        const float *W3 = sw + w.off_w3;
-        const float u = warp_sum(n0 * W3[lane * kCriticMaxOut + o] + n1 * W3[(lane + 32) * kCriticMaxOut + o]);
-        if (lane == 0) r[b * w.out + o] = u + sw[w.off_b3 + o];
+      for (int t = 0; t < kCriticMaxAgents; ++t)
+        if (t < N) {
+          score[t] = warp_sum(o0[u][t] * h0[u] + o1[u][t] * h1[u]);
+          mx = fmaxf(mx, score[t]);
+        }
+      float den = 0.0f;
+#pragma unroll
+      for (int t = 0; t < kCriticMaxAgents; ++t)
+        if (t < N) { score[t] = expf(score[t] - mx); den += score[t]; }
+      float n0 = 0.0f, n1 = 0.0f;
+#pragma unroll
+      for (int t = 0; t < kCriticMaxAgents; ++t)
+        if (t < N) {
+          const float a = score[t] / den;
+          n0 = fmaf(o0[u][t], a, n0);
+          n1 = fmaf(o1[u][t], a, n1);
+        }
+      if (w.relu_attn) { n0 = fmaxf(n0, 0.0f); n1 = fmaxf(n1, 0.0f); }  // ac_network_multi_gumbel.py:141 only
+      for (int o = 0; o < w.out; ++o) {
+        const float *W2 = sw + w.off_w2;
+        const float v = warp_sum(n0 * W2[lane * kCriticMaxOut + o] + n1 * W2[(lane + 32) * kCriticMaxOut + o]);
+        if (lane == 0 && ok[u]) q[bs[u] * w.out + o] = v + sw[w.off_b2 + o];
+        if (w.has_r && r != nullptr) {
+          const float *W3 = sw + w.off_w3;
+          const float uu = warp_sum(n0 * W3[lane * kCriticMaxOut + o] + n1 * W3[(lane + 32) * kCriticMaxOut + o]);
+          if (lane == 0 && ok[u]) r[bs[u] * w.out + o] = uu + sw[w.off_b3 + o];
+        }
       }
     }
   }
@@ -196,7 +239,7 @@ cudaError_t launch_critic_forward(const CriticDev &w, const float *obs, const fl
     have[dev] = smem;
   }
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t want = (B + kCriticWarps - 1) / kCriticWarps;
+  const int64_t want = ((B + kCriticR - 1) / kCriticR + kCriticWarps - 1) / kCriticWarps;
   const int grid = (int)(want < nsm ? want : nsm);
   k_critic_forward<<<grid, kCriticThreads, smem, st>>>(w, obs, action, B, N, q, r);
   return cudaGetLastError();
