@@ -57,6 +57,17 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.mpe_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.MPE_EINVAL
     assert lib.mpe_step(None, None, None, None, None, None, None, None, None, None) == _lib.MPE_EINVAL
     assert lib.mpe_destroy(None) == _lib.MPE_OK
+    # the round-2 entry points reject bad arguments before touching CUDA as well
+    assert lib.mpe_act_step_host_async(None, None, None, 0, None, None) == _lib.MPE_EINVAL
+    assert lib.mpe_host_block_layout(None, None) == _lib.MPE_EINVAL
+    assert lib.mpe_host_alloc(None, 0) == _lib.MPE_EINVAL and lib.mpe_host_free(None) == _lib.MPE_OK
+    assert lib.mpe_step_host_async(None, None, None, None, None, None, None) == _lib.MPE_EINVAL
+    assert lib.mpe_reset_host_async(None, None, None) == _lib.MPE_EINVAL
+    assert lib.actor_forward_host_async(None, None, 1, 3, 0, 0, 0, None, None, None, 0, None) == _lib.MPE_EINVAL
+    assert lib.critic_create(None, None) == _lib.MPE_EINVAL and lib.critic_destroy(None) == _lib.MPE_OK
+    cc = _lib.CriticConfig(obs_dim=60, act_dim=10, out_dim=1)
+    assert lib.critic_create(ctypes.byref(cc), ctypes.byref(h)) == _lib.MPE_EUNSUPPORTED
+    assert lib.critic_forward(None, None, None, 1, 3, None, None, None) == _lib.MPE_EINVAL
 
 
 def test_no_cpu_fallback():

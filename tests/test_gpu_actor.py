@@ -453,3 +453,34 @@ def test_model_head_next_state_on_both_paths(N, D, B):
         out = m.FusedActor(sd, impl=impl).forward(torch.from_numpy(obs), want_next_state=True, want_logits=True)
         assert np.abs(out['next_state'].cpu().numpy() - want['next_state']).max() <= LOGIT_ATOL * 2, impl
         assert np.abs(out['logits'].cpu().numpy() - want['logits'][0]).max() <= LOGIT_ATOL * 2, impl
+
+
+def test_host_block_layout_and_argument_checks():
+    """mpe_host_block_layout / mpe_act_step_host_async: offsets are 256 B aligned and ordered, the message head only
+    takes room when the env has one; mismatched handles are rejected, not launched."""
+    import ctypes as C
+    import multiagent_rl_b200 as m
+    from multiagent_rl_b200 import _lib
+    lib = _lib.load()
+    for scen, heads in (('simple_spread', 1), ('simple_reference', 2)):
+        env = m.make_env(scen, num_envs=1000, batched=True)
+        lay = _lib.MpeHostBlockLayout()
+        _lib.check(lib.mpe_host_block_layout(env._h, C.byref(lay)), 'layout')
+        rows = 1000 * env.n
+        offs = [lay.off_act_u, lay.off_act_c, lay.off_obs, lay.off_rew, lay.off_done, lay.bytes]
+        assert all(o % 256 == 0 for o in offs) and offs == sorted(offs)
+        assert lay.off_act_c - lay.off_act_u >= rows * 4 and lay.off_rew - lay.off_obs >= rows * env.obs_dim * 4
+        assert (lay.off_obs == lay.off_act_c) == (heads == 1)
+    env64 = m.make_env('simple_spread', num_envs=8, batched=True, precision='fp64')
+    actor = m.FusedActor(actor_ref.init_state_dict(10, 5, 0))
+    blk = _lib.HostBlock(1 << 20)
+    obs = blk.tensor((8, 3, 10), torch.float32)
+    out = blk.tensor((4096,), torch.uint8)
+    st = _lib.current_stream(actor.device)
+    assert lib.mpe_act_step_host_async(env64._h, actor._h, _lib.ptr(obs), 0, _lib.ptr(out), st) == _lib.MPE_EUNSUPPORTED
+    env6 = m.make_env('simple_spread', n=6, num_envs=8, batched=True)
+    assert lib.mpe_act_step_host_async(env6._h, actor._h, _lib.ptr(obs), 0, _lib.ptr(out), st) == _lib.MPE_EINVAL
+    assert b'observation' in lib.mpe_last_error()
+    with pytest.raises(ValueError):
+        m.HostRollout('simple_spread', 8, actor, n=6)
+    blk.free()
