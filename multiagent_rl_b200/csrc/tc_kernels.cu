@@ -973,7 +973,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
     bool tma_pending = false;  // row 0: a bulk store of the staging buffer (= the obs operand buffer) may still be reading it
     // large teams: this CTA's dense2-share scratch, [tile][half][cell][pair of head entries][row]
     f2 *scr = (kJit || kXs) ? reinterpret_cast<f2 *>(w.scratch) + (size_t)blockIdx.x * tc2_scratch_f2_per_cta(N, APAD) : nullptr;
-    mbar_wait(&bars[0], 0);
+    bool have_w = false;  // the weight image (TMA bulk load issued at kernel start) is awaited behind the first operand phase
 #ifdef MPE_TC_PHASES
     if (dbg && tid == 0 && blockIdx.x < 148) g_tc_timeline[blockIdx.x * 128 + 67] = clock64();
 #endif
@@ -1039,6 +1039,7 @@ __global__ void __launch_bounds__(tc2_threads(N), 1)
           mbar_arrive(&bars[1 + own * B_PER_WG + B_X]);
         }
 
+        if (!have_w) { mbar_wait(&bars[0], 0); have_w = true; }
         // dense2 sums of the OWN tile's rows over this thread's 16 units (+ bias), packed pairs of head entries
         constexpr int NLG = kJit ? 1 : N;
         f2 lgp[NLG][APAD / 2];
