@@ -180,3 +180,28 @@ def test_reference_bicnet_baseline_loop(ref):
     mem = keep[0].memory
     assert len(mem) == 50 and _refloop.verify_memory(mem, 'simple_spread', None) == 50
     assert len(mem._storage[0][2]) == 3 and mem._storage[0][4] == [0.0, 0.0, 0.0]
+
+
+def test_reference_optimize_learns_from_the_device_replay(ref):
+    """examples/train_batched.py: batched fused rollouts -> DeviceReplayBuffer -> the reference's Trainer.optimize()
+    (ddpg_gumbel_fix.py:131-219, unchanged) -> weights back into the fused actor.  The learner's `memory` is the device
+    ring, so process_batch (make_index / sample_index) runs on the GPU replay."""
+    import importlib.util
+    from tests.conftest import ROOT
+    spec = importlib.util.spec_from_file_location('train_batched', os.path.join(ROOT, 'examples', 'train_batched.py'))
+    tb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tb)
+    lines = []
+    returns, learner, hist = tb.train(num_envs=512, episodes=4, updates_per_episode=3, batch_size=256, log=lines.append)
+    assert len(returns) == 4 and all(np.isfinite(returns)) and len(lines) == 4
+    assert len(learner.memory) == 4 * 25 * 512
+    h = hist.history()
+    assert len(h['reward_episodes']) == 4 * 512 + 1
+    # the replay's transitions chain: obs_next of step t is obs of step t + 1 inside an episode
+    s0, a0, r, s1, d = learner.memory.sample_index(torch.arange(0, 1024, device='cuda'))
+    assert torch.equal(s1[:512], s0[512:1024]) and bool((a0.sum(-1) == 1).all()) and float(d.abs().max()) == 0.0
+    # the critic the learner trained evaluates on the device kernel too
+    import multiagent_rl_b200 as m
+    q_ref = learner.critic.forward(s0.to(learner.device), a0.to(learner.device)).detach()
+    q = m.FusedCritic(learner.critic.state_dict(), obs_dim=10).forward(s0, a0)
+    assert float((q - q_ref).abs().max()) <= 1e-4 * max(1.0, float(q_ref.abs().max()))
