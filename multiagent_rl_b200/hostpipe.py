@@ -45,6 +45,11 @@ class HostRollout(object):
     enqueueing: up to ``depth`` steps per shard are in flight and ``on_shard(shard_index, transition)`` is called for
     the step that finished ``depth`` iterations earlier - the copy engines always have the next transfer queued.
     ``flush`` delivers the transitions still in flight; ``wait`` just drains the streams.
+
+    ``depth=1`` keeps the host IN the loop: the callback for step i runs before step i + 1 is enqueued, so whatever it
+    writes into ``transition.obs`` (normalisation, masking) is what the actor sees next - at the price of one idle gap
+    per shard and step (0.75 instead of 0.83 G agent-steps/s at 65,536 envs).  ``depth=2`` (default) is for callers
+    that only consume the transitions (replay writes, statistics).
     """
 
     def __init__(self, scenario_name, num_envs, actor, shards=3, n=None, seed=0, env_id_offset=0, device=None,
