@@ -35,6 +35,8 @@ NCU_DRAM_BYTES_STEP = 221.9e6    # k_step<float,0,3>, 1,048,576 envs, rotating o
 # profiles/r2_ncu_tc2_counters.txt = 989 transcendental evaluations per env step; XU issue rate 0.5 warp inst / clk / SM
 NCU_XU_WARP_INST_FUSED = 2025472
 XU_WARP_INST_PER_CLK_PER_SM = 0.5
+# all warp instructions per launch of the same kernel (smsp__inst_executed.sum, same file); issue rate 1 / clk / sub-partition
+NCU_WARP_INST_FUSED = 26181167
 FLOPS_PER_ENV_STEP = N_AGENTS * (128 * OBS_DIM + 49152 + 128 * ACT_DIM)
 FP32_SIMT_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # FFMA peak at max clock (not a measured number)
 
@@ -408,10 +410,15 @@ def run_b200(args):
                                        'profiles/r2_ncu_full_summary_tc2_step.txt (state + weights in, outputs stay in L2)',
                      'xu_frac': (NCU_XU_WARP_INST_FUSED / kernel_s) / (148 * XU_WARP_INST_PER_CLK_PER_SM * (clk.get('sm_mhz') or 1965.0) * 1e6)
                                 if B == 65536 else None,
+                     'issue_frac': NCU_WARP_INST_FUSED / kernel_s / (148 * 4 * (clk.get('sm_mhz') or 1965.0) * 1e6)
+                                   if B == 65536 else None,
                      'xu_source': 'smsp__inst_executed_pipe_xu.sum = 2,025,472 warp instructions per launch (989 MUFU ops per '
                                   'env step), profiles/r2_ncu_tc2_counters.txt; peak = 0.5 warp inst/clk/SM x 148 SMs x the SM '
                                   'clock sampled during the run (ncu itself reads 25.9 % of XU peak over the CTA-active cycles, '
-                                  'tensor pipe 21.4 %, issue slots 41.9 % cold / 52.8 % warm)',
+                                  'tensor pipe 21.4 %, issue slots 41.9 % cold / 52.8 % warm); issue_frac = smsp__inst_executed.sum (26,181,167 warp '
+                                  'instructions per launch) / time / (4 sub-partitions x 148 SMs x the SM clock): the kernel is '
+                                  'bound by instruction issue + dependency latency at 2 epilogue warps per sub-partition, and by '
+                                  'the 13.5 % tile-quantisation tail of this batch size (DESIGN.md 4.3)',
                      'kernel': 'k_tc2<simple_spread,3,fused> (tcgen05 kind::f16, fp16 hi/lo split operands, fp32 TMEM accum)',
                      'peak_source': pk['source'] + ' bf16 sustained',
                      'flops_per_env_step': FLOPS_PER_ENV_STEP,
