@@ -530,32 +530,75 @@ __global__ void __launch_bounds__(kActorThreads, 1)
 // relu(hcat)[row][k] W3[k][j] (ac_network_model_multi_gumbel.py:49,65).  64 x D MACs per row - HBM-bound on reading
 // hcat (256 B per row), so a plain FFMA kernel: one thread per (row, output), the row's 64 inputs are broadcast loads.
 // ------------------------------------------------------------------------------------------------
+constexpr int kD3Rows = 64;  // rows per CTA tile
+template <int DQ>  // DQ = ceil(D / 4): outputs per thread
 __global__ void __launch_bounds__(256) k_dense3(ActorDev w, const float *__restrict__ hcat, int64_t rows,
                                                 float *__restrict__ next_state) {
-  const int D = w.D;
+  // A CTA stages 64 rows of relu(hcat) (16 KB, coalesced float4 loads) and the head's weights in shared memory; thread
+  // (row = tid / 4, quarter = tid % 4) then produces outputs quarter, quarter + 4, ... of its row: a row's 64 inputs are
+  // broadcast reads shared by four threads, the weights are re-laid out so that a thread's DQ weights of one k are
+  // contiguous.
+  __shared__ __align__(16) float sh[kD3Rows][kHid + 4];  // +4: rows start in different banks
+  constexpr int DQP = (DQ + 3) / 4 * 4;                  // a thread's weights of one k: DQP contiguous floats (LDS.128)
+  __shared__ __align__(16) float sw3[kHid * 4 * DQP + 4 * DQP];
+  const int D = w.D, Dpad = w.Dpad;
   const float *W3 = w.blob + w.off_w3, *b3 = w.blob + w.off_b3;
-  const int64_t total = rows * D;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / D;
-    const int j = (int)(i - row * D);
-    const float4 *h4 = reinterpret_cast<const float4 *>(hcat + row * kHid);
-    float acc = b3[j];
-#pragma unroll 4
-    for (int k4 = 0; k4 < kHid / 4; ++k4) {
-      const float4 h = h4[k4];
-      acc = fmaf(h.x, W3[(4 * k4) * w.Dpad + j], acc);
-      acc = fmaf(h.y, W3[(4 * k4 + 1) * w.Dpad + j], acc);
-      acc = fmaf(h.z, W3[(4 * k4 + 2) * w.Dpad + j], acc);
-      acc = fmaf(h.w, W3[(4 * k4 + 3) * w.Dpad + j], acc);
+  for (int i = threadIdx.x; i < kHid * 4 * DQP; i += 256) {
+    const int k = i / (4 * DQP), rem = i - k * 4 * DQP, q = rem / DQP, jj = rem - q * DQP, j = q + 4 * jj;
+    sw3[i] = (jj < DQ && j < D) ? W3[k * Dpad + j] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < 4 * DQP; i += 256) {
+    const int q = i / DQP, jj = i - q * DQP, j = q + 4 * jj;
+    sw3[kHid * 4 * DQP + i] = (jj < DQ && j < D) ? b3[j] : 0.0f;
+  }
+  const int r = threadIdx.x >> 2, qd = threadIdx.x & 3;
+  for (int64_t row0 = (int64_t)blockIdx.x * kD3Rows; row0 < rows; row0 += (int64_t)gridDim.x * kD3Rows) {
+    __syncthreads();  // weights staged / the previous tile is consumed
+    for (int i = threadIdx.x; i < kD3Rows * (kHid / 4); i += 256) {
+      const int rr = i / (kHid / 4), c4 = i - rr * (kHid / 4);
+      const float4 v = row0 + rr < rows ? reinterpret_cast<const float4 *>(hcat + (row0 + rr) * kHid)[c4]
+                                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      *reinterpret_cast<float4 *>(&sh[rr][4 * c4]) = v;
     }
-    next_state[i] = acc;
+    __syncthreads();
+    float acc[DQP];
+#pragma unroll
+    for (int jj = 0; jj < DQP; ++jj) acc[jj] = sw3[kHid * 4 * DQP + qd * DQP + jj];
+#pragma unroll 4
+    for (int k0 = 0; k0 < kHid; k0 += 4) {
+      const float4 h4 = *reinterpret_cast<const float4 *>(&sh[r][k0]);
+      const float hk[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 *wk = reinterpret_cast<const float4 *>(sw3 + ((k0 + kk) * 4 + qd) * DQP);
+#pragma unroll
+        for (int v = 0; v < DQP / 4; ++v) {
+          const float4 w4 = wk[v];
+          acc[4 * v] = fmaf(hk[kk], w4.x, acc[4 * v]);
+          if (4 * v + 1 < DQ) acc[4 * v + 1] = fmaf(hk[kk], w4.y, acc[4 * v + 1]);
+          if (4 * v + 2 < DQ) acc[4 * v + 2] = fmaf(hk[kk], w4.z, acc[4 * v + 2]);
+          if (4 * v + 3 < DQ) acc[4 * v + 3] = fmaf(hk[kk], w4.w, acc[4 * v + 3]);
+        }
+      }
+    }
+    if (row0 + r < rows) {
+#pragma unroll
+      for (int jj = 0; jj < DQ; ++jj)
+        if (qd + 4 * jj < D) next_state[(row0 + r) * D + qd + 4 * jj] = acc[jj];
+    }
   }
 }
 
 cudaError_t launch_dense3(const ActorDev &w, const float *hcat, int64_t rows, float *next_state, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  const int64_t blocks = (rows * w.D + 255) / 256;
-  k_dense3<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(w, hcat, rows, next_state);
+  const int64_t blocks = (rows + kD3Rows - 1) / kD3Rows;
+  const unsigned grid = (unsigned)(blocks < 148 * 8 ? blocks : 148 * 8);
+  switch ((w.D + 3) / 4) {
+#define D3(Q) case Q: k_dense3<Q><<<grid, 256, 0, st>>>(w, hcat, rows, next_state); break;
+    D3(1) D3(2) D3(3) D3(4) D3(5) D3(6) D3(7) D3(8) D3(9) D3(10) D3(11) D3(12) D3(13) D3(14) D3(15) D3(16)
+#undef D3
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 
