@@ -98,7 +98,8 @@ def test_reference_run_trains_on_the_cuda_env(ref, fused):
 
 
 def test_reference_run_test_loads_a_checkpoint_and_rolls_out(ref):
-    """main.py:63-65 with TEST_ONLY: run_test -> Trainer.load_models(arglist.appx + name) -> 2 episodes."""
+    """main.py:63-65 with TEST_ONLY: run_test -> Trainer.load_models(arglist.appx + name) -> 20 episodes (500 steps,
+    19 env.reset() calls in between), every transition replayed through the float64 oracle."""
     scen, run_mod, arglist = ref
     from rls.agent.multiagent.ddpg_gumbel_fix import Trainer as RefTrainer
     env = scen.make_env('simple_spread', benchmark=False, discrete_action=True, local_observation=True)
@@ -110,16 +111,19 @@ def test_reference_run_test_loads_a_checkpoint_and_rolls_out(ref):
     with torch.no_grad():
         for p in actor.parameters():
             p.add_(1.0)  # load_models must bring the saved weights back
-    arglist.num_episodes = 2
+    arglist.num_episodes = 20
     keep.clear()
     run_mod.run_test(env, actor, critic, T, 'simple_spread', action_type, cnt=0)
     learner = keep[0]
     for k, v in learner.actor.state_dict().items():
         assert torch.equal(v.cpu(), saved[k].cpu()), k
-    assert len(learner.memory) == 50 and _refloop.verify_memory(learner.memory, 'simple_spread', None) == 50
+    assert len(learner.memory) == 500 and _refloop.verify_memory(learner.memory, 'simple_spread', None) == 500
     with open('Models/test_history_simple_spread_0.pkl', 'rb') as fp:
         hist = pickle.load(fp)
-    assert len(hist['reward_episodes']) == 3 and len(hist['memory']) == 50
+    assert len(hist['reward_episodes']) == 21 and len(hist['memory']) == 500
+    # every episode starts from a fresh numpy-drawn state: the first observations of consecutive episodes differ
+    starts = [np.stack(learner.memory._storage[25 * e][0]) for e in range(20)]
+    assert all(not np.array_equal(starts[e], starts[e + 1]) for e in range(19))
 
 
 @pytest.mark.parametrize('n', [6, 12])
