@@ -13,8 +13,12 @@ Parity status (see DESIGN.md "Oracle"):
     pinned and not installable offline; the reference ships no tests or golden
     vectors.  The restatement follows the published upstream algorithm
     function by function and is anchored on hand-derived known answers.
-  * observations (``local_obs_*``): follow /root/reference/experiments/scenarios.py:6-63.
+  * observations (``local_obs_*``) and ``make_env``: follow /root/reference/experiments/scenarios.py:6-63,124-192
+    and are **pinned by execution**: ``python -m oracle.build_ref`` byte-compiles the reference's modules into
+    ``oracle/_ref`` and tests/test_reference_exec.py runs the reference's own ``make_env`` against this package
+    (bit-exact on all fixtures).
   * actor forward (``actor_ref``): **pinned** against the reference's own
     ``rls.model.ac_network_multi_gumbel.ActorNetwork`` run in the authoring
-    container (``oracle/gen_golden.py`` -> ``tests/golden/actor_*.npz``).
+    container (``oracle/gen_golden.py`` -> ``tests/golden/actor_*.npz``); critic forward (``critic_ref``) likewise
+    (``tests/golden/critic_*.npz``).
 """

@@ -19,6 +19,24 @@ What IS taken from the reference tree:
     ``world.collaborative = False`` (:171), ``force_discrete_action = True``
     (:191), ``discrete_action=True`` (:182-190), ``make_world(num_agents=n)`` (:170).
 
+EXECUTED-REFERENCE vs RESTATED-UPSTREAM (round 2), by line range of this file:
+  * ``SimpleSpread.observation`` / ``SimpleReference.observation`` /
+    ``SimpleSpeakerListener.observation`` (the three ``def observation`` bodies) and
+    ``make_env`` (the last function): restatements of code that IS in the reference
+    tree, now PINNED by executing the reference's own functions - the reference's
+    ``experiments/scenarios.py`` is byte-compiled into oracle/_ref by
+    ``python -m oracle.build_ref`` and run on tests/_stubs/multiagent;
+    tests/test_reference_exec.py::test_reference_make_env_equals_the_oracle_bit_for_bit
+    requires bit equality of observations, rewards and benchmark flags with this
+    file and with the committed fixtures, for all six scenario / team-size files.
+  * everything else (``World.*``, ``MultiAgentEnv.*``, ``reset_world`` / ``reward`` /
+    ``benchmark_data`` / ``make_world`` of the three scenarios): restated upstream,
+    NOT executable from the reference tree - parity unpinned.  The reference's own
+    loops (experiments/run.py, run_BIC.py) and Trainers are executed on top of it
+    (tests/test_reference_exec.py, tests/test_gpu_reference_loop.py), which pins
+    the CALL contract (argument shapes, in-place one-hot rewrite, reset order,
+    return types), not the arithmetic.
+
 Version ambiguities (recorded per SURVEY.md section 8c):
   1. OpenAI vs MAAC fork: identical arithmetic for mass 1, accel None, no walls.
   2. ``make_world(num_agents=n)`` is not in stock simple_spread; we assume
