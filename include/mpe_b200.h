@@ -34,7 +34,8 @@ extern "C" {
 #define MPE_ABI_VERSION 2
 
 enum { MPE_OK = 0, MPE_EINVAL = -1, MPE_ECUDA = -2, MPE_EUNSUPPORTED = -3 };
-enum { MPE_SIMPLE_SPREAD = 0, MPE_SIMPLE_REFERENCE = 1, MPE_SIMPLE_SPEAKER_LISTENER = 2 };
+enum { MPE_SIMPLE_SPREAD = 0, MPE_SIMPLE_REFERENCE = 1, MPE_SIMPLE_SPEAKER_LISTENER = 2,
+       MPE_COLLECT_TREASURE = 3 /* fullobs_collect_treasure, main.py:24-25; 6 collectors + 2 deposits, 6 treasures */ };
 enum { MPE_F32 = 0, MPE_F64 = 1 };
 
 typedef struct MpeEnv MpeEnv;     /* one shard of env instances on one GPU */

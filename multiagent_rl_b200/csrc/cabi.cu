@@ -122,6 +122,10 @@ int mpe_create(const MpeConfig *cfg, MpeEnv **out) {
       if (N != 0 && N != 2) return fail(MPE_EUNSUPPORTED, "simple_speaker_listener has exactly 2 agents");
       N = 2; L = 3; D = 11; dimc = 3;
       break;
+    case MPE_COLLECT_TREASURE:  // MAAC fork: make_world() takes no agent count (8 agents: 6 collectors + 2 deposits)
+      if (N != 0 && N != 8) return fail(MPE_EUNSUPPORTED, "fullobs_collect_treasure has exactly 8 agents");
+      N = 8; L = 6; D = 30; dimc = 2;
+      break;
     default:
       return fail(MPE_EUNSUPPORTED, "mpe_create: unknown scenario");
   }
@@ -138,6 +142,10 @@ int mpe_create(const MpeConfig *cfg, MpeEnv **out) {
   mpe::EnvStateAny &s = env->st;
   s.B = cfg->num_envs; s.gid0 = cfg->env_id_offset; s.seed = cfg->seed;
   s.max_speed = cfg->max_speed; s.accel = cfg->accel;
+  if (cfg->scenario == MPE_COLLECT_TREASURE) {  // the scenario sets accel = 1.5 and max_speed = 1.0 on every agent
+    if (s.max_speed < 0.0) s.max_speed = 1.0;
+    if (s.accel < 0.0) s.accel = 1.5;
+  }
   s.precision = cfg->precision; s.scenario = cfg->scenario;
   s.N = N; s.L = L; s.D = D; s.dimc = dimc; s.act_u = 5; s.act_c = act_c;
   s.max_episode_len = cfg->max_episode_len > 0 ? cfg->max_episode_len : 0;
@@ -834,6 +842,7 @@ int replay_sample(MpeReplay *r, int64_t batch, const int64_t *idx, uint64_t seed
 namespace mpe {
 bool env_supported(int scenario, int N) {
   if (scenario == 0) return N >= 1 && N <= 12;  // simple_spread: make_world(num_agents=n), experiments/scenarios.py:170
+  if (scenario == 3) return N == 8;  // fullobs_collect_treasure
   return (scenario == 1 || scenario == 2) && N == 2;
 }
 cudaError_t launch_reset(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st) {

@@ -20,7 +20,7 @@
 
 namespace mpe {
 
-enum : int { kSpread = 0, kReference = 1, kSpeaker = 2 };
+enum : int { kSpread = 0, kReference = 1, kSpeaker = 2, kTreasure = 3 };  // kTreasure: env_treasure.cuh
 
 template <int SC, int N_>
 struct Dims {
@@ -57,6 +57,9 @@ struct EnvState {
   T t2_coll;          // sqrt(d2) < dist_min (0.30)          is_collision
   T t2_occ;           // sqrt(d2) < 0.1                      occupied landmark
   T t2_cut;           // sqrt(d2) > dist_min + underflow     contact force is exactly 0 beyond
+  // fullobs_collect_treasure (env_treasure.cuh): contacts collector-collector / collector-deposit / collector-treasure,
+  // force cut-offs collector-collector / collector-deposit / deposit-deposit
+  T tr_t2[3], tr_cut[3];
 };
 
 // smallest x with sqrt(x) >= c  (so that  sqrt(d2) < c  <=>  d2 < x); host, IEEE sqrt
@@ -139,6 +142,16 @@ inline void set_thresholds(EnvState<T> &s, int scenario) {
   s.t2_coll = sqrt_lt_threshold<T>(dist_min);
   s.t2_occ = sqrt_lt_threshold<T>((T)0.1);
   s.t2_cut = sqrt_gt_threshold<T>(dist_min + Underflow<T>::v);
+  for (int k = 0; k < 3; ++k) s.tr_t2[k] = s.tr_cut[k] = (T)0;
+  if (scenario == kTreasure) {  // sizes: collector 0.05, deposit 0.075, treasure 0.025 (sums taken in double like numpy)
+    const double cc = 0.05 + 0.05, cd = 0.05 + 0.075, ct = 0.05 + 0.025, dd = 0.075 + 0.075;
+    s.tr_t2[0] = sqrt_lt_threshold<T>((T)cc);
+    s.tr_t2[1] = sqrt_lt_threshold<T>((T)cd);
+    s.tr_t2[2] = sqrt_lt_threshold<T>((T)ct);
+    s.tr_cut[0] = sqrt_gt_threshold<T>((T)cc + Underflow<T>::v);
+    s.tr_cut[1] = sqrt_gt_threshold<T>((T)cd + Underflow<T>::v);
+    s.tr_cut[2] = sqrt_gt_threshold<T>((T)dd + Underflow<T>::v);
+  }
 }
 
 // get_collision_force for one close pair: (gx, gy) = contact_force * delta / dist * penetration.

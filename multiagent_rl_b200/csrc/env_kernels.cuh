@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(kStepThreads)
 
 }  // namespace mpe
 #include "env_group.cuh"
+#include "env_treasure.cuh"
 namespace mpe {
 
 // ---------------------------------------------------------------------------------------------
@@ -252,7 +253,7 @@ namespace mpe {
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void k_set_state(EnvState<T> s, int N, int L, int dimc, const T *pos, const T *vel, const T *lm,
-                            const int32_t *goal) {
+                            const int32_t *goal, int raw_goal) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B) return;
   for (int i = 0; i < N; ++i) {
@@ -267,14 +268,14 @@ __global__ void k_set_state(EnvState<T> s, int N, int L, int dimc, const T *pos,
     }
   if (goal != nullptr && s.goal != nullptr) {
     const int g0 = goal[b * N], g1 = N > 1 ? goal[b * N + 1] : -1;
-    s.goal[b] = (g0 & 0xFF) | ((g1 & 0xFF) << 8);
+    s.goal[b] = raw_goal ? g0 : ((g0 & 0xFF) | ((g1 & 0xFF) << 8));  // raw: the treasure scenario's state word
   }
   if (s.comm != nullptr)
     for (int k = 0; k < N * dimc; ++k) s.comm[(int64_t)k * s.B + b] = (T)0;
 }
 
 template <typename T>
-__global__ void k_get_state(EnvState<T> s, int N, int L, T *pos, T *vel, T *lm, int32_t *goal) {
+__global__ void k_get_state(EnvState<T> s, int N, int L, T *pos, T *vel, T *lm, int32_t *goal, int raw_goal) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= s.B) return;
   for (int i = 0; i < N; ++i) {
@@ -289,7 +290,9 @@ __global__ void k_get_state(EnvState<T> s, int N, int L, T *pos, T *vel, T *lm, 
     }
   if (goal != nullptr) {
     for (int i = 0; i < N; ++i) goal[b * N + i] = -1;
-    if (s.goal != nullptr) {
+    if (s.goal != nullptr && raw_goal) {
+      goal[b * N] = s.goal[b];
+    } else if (s.goal != nullptr) {
       const int32_t g = s.goal[b];
       const int g0 = g & 0xFF, g1 = (g >> 8) & 0xFF;
       goal[b * N] = g0 == 0xFF ? -1 : g0;
@@ -384,9 +387,23 @@ inline cudaError_t set_smem_once(int bytes) {
     return cudaGetLastError();                                                                                     \
   }
 
+// fullobs_collect_treasure: one kernel template, MODE = step / reset / observe (env_treasure.cuh)
+template <typename T, int MODE>
+cudaError_t launch_treasure_t(const EnvStateAny &a, const int32_t *act_u, const uint8_t *mask, int auto_len, void *obs,
+                              void *rew, uint8_t *done, int32_t *info_i, cudaStream_t st) {
+  constexpr int sm = TrLayout<T>::kBlockBytes;
+  cudaError_t err = set_smem_once<k_treasure<T, MODE>>(sm);
+  if (err != cudaSuccess) return err;
+  const unsigned grid = (unsigned)((a.B + kStepThreads - 1) / kStepThreads);
+  k_treasure<T, MODE><<<grid, kStepThreads, sm, st>>>(typed<T>(a), act_u, mask, auto_len, static_cast<T *>(obs),
+                                                      static_cast<T *>(rew), done, info_i);
+  return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs, int auto_len, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
+  if (a.scenario == kTreasure) return launch_treasure_t<T, 1>(a, nullptr, mask, auto_len, obs, nullptr, nullptr, nullptr, st);
   if (a.scenario == kSpread && group_lanes(a.N) > 0) {  // G lanes per env (env_group.cuh)
 #define GRP(NN, GG) MPE_GRP_RESET(NN, GG, 1)
     MPE_DISPATCH_GRP(a, GRP);
@@ -408,6 +425,7 @@ cudaError_t launch_reset_t(const EnvStateAny &a, const uint8_t *mask, void *obs,
 template <typename T>
 cudaError_t launch_observe_t(const EnvStateAny &a, void *obs, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
+  if (a.scenario == kTreasure) return launch_treasure_t<T, 2>(a, nullptr, nullptr, 0, obs, nullptr, nullptr, nullptr, st);
   if (a.scenario == kSpread && group_lanes(a.N) > 0) {
     const uint8_t *mask = nullptr;
     const int auto_len = 0;
@@ -432,6 +450,7 @@ template <typename T>
 cudaError_t launch_step_t(const EnvStateAny &a, const int32_t *act_u, const int32_t *act_c, const void *comm_vec,
                           void *obs, void *rew, uint8_t *done, int32_t *info_i, void *info_f, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
+  if (a.scenario == kTreasure) return launch_treasure_t<T, 0>(a, act_u, nullptr, 0, obs, rew, done, info_i, st);
   if (a.scenario == kSpread && group_lanes(a.N) > 0) {  // G lanes per env (env_group.cuh)
 #define GRP(NN, GG)                                                                                                \
   {                                                                                                                \
@@ -468,7 +487,8 @@ cudaError_t launch_set_state_t(const EnvStateAny &a, const void *pos, const void
   if (a.B <= 0) return cudaSuccess;
   const unsigned grid = (unsigned)((a.B + 255) / 256);
   k_set_state<T><<<grid, 256, 0, st>>>(typed<T>(a), a.N, a.L, a.dimc, static_cast<const T *>(pos),
-                                       static_cast<const T *>(vel), static_cast<const T *>(lm), goal);
+                                       static_cast<const T *>(vel), static_cast<const T *>(lm), goal,
+                                       a.scenario == kTreasure ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -477,7 +497,7 @@ cudaError_t launch_get_state_t(const EnvStateAny &a, void *pos, void *vel, void 
   if (a.B <= 0) return cudaSuccess;
   const unsigned grid = (unsigned)((a.B + 255) / 256);
   k_get_state<T><<<grid, 256, 0, st>>>(typed<T>(a), a.N, a.L, static_cast<T *>(pos), static_cast<T *>(vel),
-                                       static_cast<T *>(lm), goal);
+                                       static_cast<T *>(lm), goal, a.scenario == kTreasure ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -1633,7 +1633,7 @@ static cudaError_t launch_tc_t(const EnvState<float> &s, const TcDev &w, const A
 
 bool tc_actor_supported(const TcDev &w, int N) {
   // teams of > 3 agents keep one head of <= 8 entries (launch_actor_forward_tc); wider heads go to the FFMA kernel
-  return tc_supported(w) && (N == 2 || N == 3 || ((N == 4 || N == 6 || N == 9 || N == 12) && w.A <= 8 && w.scratch != nullptr));
+  return tc_supported(w) && (N == 2 || N == 3 || ((N == 4 || N == 6 || N == 8 || N == 9 || N == 12) && w.A <= 8 && w.scratch != nullptr));
 }
 bool tc_rollout_supported(const TcDev &w, int N) {
   // one kernel for all T steps: teams of <= 3 (every agent of an env in one thread's registers) and the large
@@ -1663,6 +1663,7 @@ cudaError_t launch_actor_forward_tc(const TcDev &w, const ActorIO &io, cudaStrea
                         : launch_tc_t<kSpread, 3, false, 8>(s, w, io, ro, 0, io.B, st);
     case 4: return wide ? cudaErrorInvalidValue : launch_tc_t<kSpread, 4, false, 8>(s, w, io, ro, 0, io.B, st);
     case 6: return wide ? cudaErrorInvalidValue : launch_tc_t<kSpread, 6, false, 8>(s, w, io, ro, 0, io.B, st);
+    case 8: return wide ? cudaErrorInvalidValue : launch_tc_t<kSpread, 8, false, 8>(s, w, io, ro, 0, io.B, st);
     case 9: return wide ? cudaErrorInvalidValue : launch_tc_t<kSpread, 9, false, 8>(s, w, io, ro, 0, io.B, st);
     case 12: return wide ? cudaErrorInvalidValue : launch_tc_t<kSpread, 12, false, 8>(s, w, io, ro, 0, io.B, st);
     default: return cudaErrorInvalidValue;

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 from .spaces import Box, Discrete, MultiDiscrete
 
-SCENARIOS = ('simple_spread', 'simple_reference', 'simple_speaker_listener')
+SCENARIOS = ('simple_spread', 'simple_reference', 'simple_speaker_listener', 'fullobs_collect_treasure')
 
 
 class _World(object):
@@ -145,6 +145,20 @@ class BatchedMultiAgentEnv(object):
         idx = range(B) if mask is None else [b for b in range(B) if mask[b]]
         pos, vel, lm, goal = self.get_state()
         pos, vel, lm, goal = pos.cpu().numpy(), vel.cpu().numpy(), lm.cpu().numpy(), goal.cpu().numpy()
+        if self.scenario_name == 'fullobs_collect_treasure':
+            # MAAC fork reset_world: agents, then per treasure its type (np.random.choice) and its position
+            for b in idx:
+                for i in range(N):
+                    pos[b, i] = np.random.uniform(low=-1, high=1, size=2)
+                    vel[b, i] = 0.0
+                types = 0
+                for l in range(L):
+                    types |= int(np.random.choice(2)) << l
+                    lm[b, l] = np.random.uniform(low=-0.95, high=0.95, size=2)
+                goal[b, 0] = types | (0x3F << 6)  # all alive, nobody holds anything
+            self.set_state(pos, vel, lm, goal)
+            self._tr_flags = goal[:, 0].copy()
+            return
         for b in idx:
             if self.scenario_name == 'simple_reference':
                 goal[b, 0] = np.random.choice(L)
@@ -198,6 +212,8 @@ class BatchedMultiAgentEnv(object):
         obs, rew, done, info = self.step_tensor(torch.from_numpy(act_u), None,
                                                 comm_vec=comm if self.act_c > 0 else None, info=self.benchmark)
         self.time += 1
+        if self.scenario_name == 'fullobs_collect_treasure' and self.rng == 'numpy':
+            self._respawn_numpy()
         o = obs.detach().to('cpu', torch.float64).numpy()
         r = rew.detach().to('cpu', torch.float64).numpy()
         obs_n = [o[0, i].copy() for i in range(N)]
@@ -207,6 +223,9 @@ class BatchedMultiAgentEnv(object):
             ii = info['info_i'].cpu().numpy()
             md = float(info['info_f'].cpu().numpy()[0])
             info_n = {'n': [(rew_n[i], int(ii[0, i]), md, int(ii[0, N])) for i in range(N)]}
+        elif self.benchmark and self.scenario_name == 'fullobs_collect_treasure':
+            ii = info['info_i'].cpu().numpy()
+            info_n = {'n': [int(ii[0, i]) for i in range(N)]}
         elif self.benchmark:
             info_n = {'n': [rew_n[i] for i in range(N)]}
         else:
@@ -214,6 +233,26 @@ class BatchedMultiAgentEnv(object):
         if self.shared_reward:  # upstream MultiAgentEnv.step: world.collaborative -> every agent gets the sum
             rew_n = [np.sum(rew_n)] * N
         return obs_n, rew_n, done_n, info_n
+
+    def _respawn_numpy(self):
+        """rng='numpy' (the one-env drop-in): the treasures that post_step respawned in this step (dead one step
+        earlier) get the draws upstream would have taken from numpy's GLOBAL generator, in upstream's order per
+        treasure: probability, position, type."""
+        prev = getattr(self, '_tr_flags', None)
+        pos, vel, lm, goal = self.get_state()
+        lm, goal = lm.cpu().numpy(), goal.cpu().numpy()
+        if prev is not None:
+            changed = False
+            for b in range(self.num_envs):
+                for l in range(self.num_landmarks):
+                    if not (int(prev[b]) >> (6 + l)) & 1:
+                        np.random.uniform()  # <= respawn_prob (1.0)
+                        lm[b, l] = np.random.uniform(low=-0.95, high=0.95, size=2)
+                        goal[b, 0] = (int(goal[b, 0]) & ~(1 << l)) | (int(np.random.choice(2)) << l)
+                        changed = True
+            if changed:
+                self.set_state(None, None, lm, goal)
+        self._tr_flags = goal[:, 0].copy()
 
     # ------------------------------------------------------------------ tensor surface
     def step_tensor(self, act_u, act_c=None, comm_vec=None, out=None, info=False):

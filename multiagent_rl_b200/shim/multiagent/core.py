@@ -9,4 +9,5 @@ class World(object):
         self.collaborative = True   # stock scenarios set True; experiments/scenarios.py:171 overwrites with False
         self.dim_p = 2
         self.dim_color = 3
-        self.dim_c = {'simple_spread': 2, 'simple_reference': 10, 'simple_speaker_listener': 3}[scenario_name]
+        self.dim_c = {'simple_spread': 2, 'simple_reference': 10, 'simple_speaker_listener': 3,
+                      'fullobs_collect_treasure': 2}[scenario_name]

@@ -91,6 +91,79 @@ def gen_mpe(scenario, n, B, seed):
     print('wrote', name, 'contacts:', int((coll.sum(-1) > N).sum()))
 
 
+TREASURE_SEED = 20240607  # Philox key of the fixture's respawn draws (global env id = row index, episode 0)
+
+
+def gen_treasure(B, seed, T=T):
+    """``mpe_fullobs_collect_treasure.npz``: the loop oracle of the MAAC-fork scenario (oracle/maac_ref.py) from
+    crafted initial states - collectors on / next to treasures, collectors that hold a treasure next to the matching
+    (and the wrong) deposit, a dead treasure that respawns in the first post_step, agents in contact across the three
+    mass pairings - under seeded random actions.  Respawn draws come from the kernels' Philox stream
+    (seed TREASURE_SEED, env id = row, episode 0, step t), so a CUDA env seeded alike reproduces the file."""
+    from oracle import maac_ref, mpe_ref
+    rng = np.random.RandomState(seed)
+    env = mpe_ref.make_env('fullobs_collect_treasure')
+    bench = mpe_ref.make_env('fullobs_collect_treasure', benchmark=True)
+    N, L, D = 8, 6, 30
+    pos0 = rng.uniform(-1, 1, (B, N, 2)); vel0 = np.zeros((B, N, 2))
+    tr0 = rng.uniform(-0.95, 0.95, (B, L, 2))
+    flags0 = np.zeros(B, dtype=np.int64)
+    for b in range(B):
+        types = rng.randint(0, 2, L); alive = [True] * L; hold = [-1] * 6
+        kind = b % 6
+        if kind == 1:    # collectors right at treasures (inside / just outside the 0.075 contact radius)
+            for i in range(6):
+                ang = rng.uniform(0, 2 * np.pi)
+                pos0[b, i] = tr0[b, rng.randint(L)] + rng.uniform(0.0, 0.12) * np.array([np.cos(ang), np.sin(ang)])
+        elif kind == 2:  # holders next to the deposits
+            for i in range(6):
+                hold[i] = int(rng.randint(-1, 2))
+                ang = rng.uniform(0, 2 * np.pi)
+                pos0[b, i] = pos0[b, 6 + rng.randint(2)] + rng.uniform(0.0, 0.2) * np.array([np.cos(ang), np.sin(ang)])
+        elif kind == 3:  # dead treasures (they respawn in the first post_step), some holders
+            for l in rng.choice(L, 2, replace=False):
+                alive[l] = False
+                tr0[b, l] = -999.0
+            hold[0] = int(types[0])
+        elif kind == 4:  # contacts between collectors, collector / deposit and the two deposits; moving agents
+            pos0[b, 1] = pos0[b, 0] + np.array([0.09, 0.01])
+            pos0[b, 2] = pos0[b, 6] + np.array([0.05, 0.1])
+            pos0[b, 7] = pos0[b, 6] + np.array([-0.1, 0.1])
+            vel0[b] = rng.uniform(-1.2, 1.2, (N, 2))
+        elif kind == 5:  # everything at once
+            vel0[b] = rng.uniform(-0.5, 0.5, (N, 2))
+            for i in range(6):
+                hold[i] = int(rng.randint(-1, 2))
+                pos0[b, i] = (tr0[b, i] if hold[i] < 0 else pos0[b, 6 + hold[i]]) + rng.uniform(-0.08, 0.08, 2)
+        flags0[b] = maac_ref.pack_flags(types, alive, hold)
+    act_u = rng.randint(0, 5, (T, B, N))
+    pos = np.zeros((T, B, N, 2)); vel = np.zeros((T, B, N, 2)); tr = np.zeros((T, B, L, 2))
+    obs = np.zeros((T, B, N, D)); rew = np.zeros((T, B, N)); flags = np.zeros((T, B), dtype=np.int64)
+    info = np.zeros((T, B, N), dtype=np.int32); obs0 = np.zeros((B, N, D))
+    for b in range(B):
+        for e in (env, bench):
+            e.scenario.draws = maac_ref.PhiloxDraws(TREASURE_SEED, b)
+            maac_ref.set_state(e, pos0[b], vel0[b], tr0[b], flags0[b])
+        obs0[b] = np.stack(mpe_ref.get_obs(env))
+        for t in range(T):
+            for e in (env, bench):
+                e.scenario.draws.tstep = t
+            acts = [np.eye(5)[act_u[t, b, i]] for i in range(N)]
+            o, r, d, _ = env.step([a.copy() for a in acts])
+            o2, r2, _, inf = bench.step([a.copy() for a in acts])
+            assert r == r2 and not any(d)
+            obs[t, b] = np.stack(o); rew[t, b] = np.array(r); info[t, b] = np.array(inf['n'])
+            pos[t, b] = np.stack([a.state.p_pos for a in env.world.agents])
+            vel[t, b] = np.stack([a.state.p_vel for a in env.world.agents])
+            tr[t, b] = np.stack([l.state.p_pos for l in env.world.landmarks])
+            flags[t, b] = maac_ref.get_flags(env)
+    name = 'mpe_fullobs_collect_treasure.npz'
+    np.savez_compressed(os.path.join(GOLD, name), pos0=pos0, vel0=vel0, tr0=tr0, flags0=flags0, act_u=act_u, obs0=obs0,
+                        pos=pos, vel=vel, tr=tr, obs=obs, rew=rew, flags=flags, info=info, seed=np.int64(TREASURE_SEED))
+    ev = (np.diff(np.concatenate([flags0[None], flags]), axis=0) != 0).sum()
+    print('wrote', name, 'state-word changes (pick-up / respawn / deposit):', int(ev), 'reward range', rew.min(), rew.max())
+
+
 def gen_actor(tag, D, A, N, B, seed, model_head):
     sys.path.insert(0, '/root/reference')
     import torch
@@ -178,6 +251,7 @@ def main():
     gen_mpe('simple_spread', 12, 12, 104)
     gen_mpe('simple_reference', None, 48, 105)
     gen_mpe('simple_speaker_listener', None, 48, 106)
+    gen_treasure(48, 107)
     if os.path.isdir('/root/reference'):
         gen_actor('spread_n3', 10, 5, 3, 256, 12345678, False)
         gen_actor('spread_n12', 28, 5, 12, 64, 12345679, False)

@@ -521,8 +521,6 @@ class MultiAgentEnv(object):
         for i, agent in enumerate(self.agents):
             self._set_action(action_n[i], agent, self.action_space[i])
         self.world.step()
-        if self.post_step_callback is not None:
-            self.post_step_callback(self.world)
         for agent in self.agents:
             obs_n.append(self._get_obs(agent))
             reward_n.append(self._get_reward(agent))
@@ -531,6 +529,10 @@ class MultiAgentEnv(object):
         reward = np.sum(reward_n)
         if self.shared_reward:
             reward_n = [reward] * self.n
+        # MAAC fork: the scenario hook runs after the step's observations and rewards were taken (None for the
+        # three stock scenarios; oracle/maac_ref.py, ambiguity 1, for fullobs_collect_treasure)
+        if self.post_step_callback is not None:
+            self.post_step_callback(self.world)
         return obs_n, reward_n, done_n, info_n
 
     def reset(self):
@@ -615,6 +617,8 @@ def make_env(scenario_name, n=None, local_observation=True, benchmark=False, dis
     classes here always use the reference's partial observations (that is the
     only branch main.py:39 and main_scalability_1.py:36 take).
     """
+    if scenario_name == 'fullobs_collect_treasure':
+        from . import maac_ref  # noqa: F401  (registers the MAAC-fork scenario)
     if scenario_name not in SCENARIOS:
         raise ValueError('unsupported scenario: %r' % (scenario_name,))
     scenario = SCENARIOS[scenario_name]()
@@ -627,7 +631,7 @@ def make_env(scenario_name, n=None, local_observation=True, benchmark=False, dis
     env = MultiAgentEnv(world, reset_callback=scenario.reset_world,
                         reward_callback=scenario.reward,
                         observation_callback=scenario.observation,
-                        post_step_callback=None,
+                        post_step_callback=getattr(scenario, 'post_step', None),  # scenarios.py:174-177
                         info_callback=scenario.benchmark_data if benchmark else None,
                         discrete_action=discrete_action,
                         uniform_action_width=uniform)

@@ -21,6 +21,11 @@ Stream layout (must match multiagent_rl_b200/csrc/common.cuh):
   domain 3 = Gumbel noise, t = global step index, slot = agent * 8 + j: call j gives noise
              for head entries 4j..4j+3 of that agent's concatenated logits.
              u = ((r >> 9) + 0.5) * 2^-23 ;  g = -log(-log(u)).
+  fullobs_collect_treasure (csrc/env_treasure.cuh):
+  domain 1 = as above over 8 agents + 6 treasures; treasure positions are scaled by 0.95.
+  domain 2 = treasure types at reset, t = episode: slot 0 gives types 0..3, slot 1 types 4, 5 ; type = r >> 31.
+  domain 4 = respawn, t = episode, slot = (step within the episode & 0xFFF) << 4 | treasure:
+             r0, r1 -> position (scaled by 0.95), r2 >> 31 -> type, r3 -> the probability draw (prob = 1: passes).
 """
 import numpy as np
 
@@ -33,6 +38,7 @@ MASK = np.uint64(0xFFFFFFFF)
 DOMAIN_RESET = 1
 DOMAIN_GOAL = 2
 DOMAIN_GUMBEL = 3
+DOMAIN_RESPAWN = 4
 
 
 def philox4x32_10(counter, key):
@@ -113,3 +119,22 @@ def gumbel_noise(seed, gid, step, n_agents, width, dtype=np.float64):
                 if 4 * j + q < width:
                     out[..., a, 4 * j + q] = bits_to_gumbel(r[q], dtype)
     return out
+
+
+def treasure_reset(seed, gid, episode):
+    """fullobs_collect_treasure reset -> (agent pos [B,8,2], treasure pos [B,6,2], treasure types [B,6])."""
+    pos = reset_positions(seed, gid, episode, 14)
+    gid = np.asarray(gid, dtype=np.uint64)
+    episode = np.broadcast_to(np.asarray(episode, dtype=np.uint64), gid.shape)
+    r0 = raw(seed, gid, episode, DOMAIN_GOAL, 0)
+    r1 = raw(seed, gid, episode, DOMAIN_GOAL, 1)
+    types = np.stack([(x >> np.uint32(31)).astype(np.int64) for x in (r0[0], r0[1], r0[2], r0[3], r1[0], r1[1])], axis=-1)
+    return pos[..., :8, :], pos[..., 8:, :] * 0.95, types
+
+
+def treasure_respawn(seed, gid, episode, tstep, treasure):
+    """-> (position [.., 2], type) of a treasure that respawns in post_step of step `tstep` of episode `episode`."""
+    slot = ((np.asarray(tstep, dtype=np.uint64) & np.uint64(0xFFF)) << np.uint64(4)) | np.asarray(treasure, dtype=np.uint64)
+    r = raw(seed, gid, episode, DOMAIN_RESPAWN, slot)
+    pos = np.stack([bits_to_pos(r[0]), bits_to_pos(r[1])], axis=-1) * 0.95
+    return pos, (r[2] >> np.uint32(31)).astype(np.int64)

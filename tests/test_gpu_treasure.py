@@ -1,0 +1,299 @@
+"""GPU parity of fullobs_collect_treasure (csrc/env_treasure.cuh) against oracle/maac_ref.py and the
+committed fixture tests/golden/mpe_fullobs_collect_treasure.npz, through the C ABI.
+
+Tolerances.  fp64 build: 1e-12 abs on positions / observations / rewards, the state word (types, alive, holding) and
+the benchmark flags bit-exact.  fp32 build, one step from the fixture's float64 state: 2e-6 on positions and
+observations, 1e-5 on rewards; a state word / flag / treasure order may differ only where the deciding float64
+distance lies within 1e-6 of its threshold (or of the next treasure's distance)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import actor_ref, build_ref, maac_ref, mpe_ref, philox
+
+pytestmark = pytest.mark.gpu
+SC = 'fullobs_collect_treasure'
+
+
+def _gold(golden_dir):
+    return np.load(os.path.join(golden_dir, 'mpe_fullobs_collect_treasure.npz'))
+
+
+def _make(B, precision='fp32', seed=1, **kw):
+    import multiagent_rl_b200 as m
+    return m.make_env(SC, num_envs=B, batched=True, precision=precision, seed=seed, **kw)
+
+
+def _set(env, pos, vel, tr, flags):
+    goal = np.zeros((len(flags), 8), dtype=np.int32)
+    goal[:, 0] = flags
+    env.set_state(pos, vel, tr, goal)
+
+
+def _flags(env):
+    return env.get_state()[3][:, 0].cpu().numpy().astype(np.int64)
+
+
+def test_dims_and_spaces():
+    env = _make(5)
+    assert env.n == 8 and env.num_landmarks == 6 and env.obs_dim == 30 and env.act_c == 0
+    assert all(s.n == 5 for s in env.action_space) and env.observation_space[0].shape == (30,)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_philox_reset_is_bit_exact(precision):
+    B, seed = 1000, 77
+    env = _make(B, precision, seed=seed, env_id_offset=10_000)
+    gid = np.arange(B) + 10_000
+    for episode in range(2):
+        obs = env.reset()
+        pos, vel, tr, goal = env.get_state()
+        a, t, ty = philox.treasure_reset(seed, gid, episode)
+        assert np.array_equal(pos.cpu().numpy(), a) and not vel.any()
+        if precision == 'fp64':
+            assert np.array_equal(tr.cpu().numpy(), t)
+        else:
+            assert np.array_equal(tr.cpu().numpy(), (t / 0.95).astype(np.float32) * np.float32(0.95))
+        want = np.array([maac_ref.pack_flags(ty[b], [True] * 6, [-1] * 6) for b in range(B)])
+        assert np.array_equal(goal[:, 0].cpu().numpy(), want)
+        # the observation of a fresh episode: own position, zero velocity, nothing held
+        o = obs.cpu().numpy()
+        assert np.array_equal(o[:, :, 0:2], pos.cpu().numpy()) and not o[:, :, 2:6].any()
+
+
+def test_fp64_build_reproduces_the_fixture(golden_dir):
+    """25 steps from the crafted states (pick-ups, deposits, respawns from the Philox stream, the three mass
+    pairings in contact, max_speed clipping): every channel against the loop oracle's committed output."""
+    g = _gold(golden_dir)
+    T, B = g['act_u'].shape[:2]
+    env = _make(B, 'fp64', seed=int(g['seed']))
+    env.reset()                      # episode 0, step counter 0: the keys of the fixture's respawn draws
+    _set(env, g['pos0'], g['vel0'], g['tr0'], g['flags0'])
+    assert np.abs(env.observe().cpu().numpy() - g['obs0']).max() <= 1e-12
+    for t in range(T):
+        obs, rew, done, info = env.step(torch.from_numpy(g['act_u'][t].astype(np.int32)), info=True)
+        pos, vel, tr, goal = env.get_state()
+        assert np.abs(pos.cpu().numpy() - g['pos'][t]).max() <= 1e-12, t
+        assert np.abs(vel.cpu().numpy() - g['vel'][t]).max() <= 1e-12, t
+        assert np.abs(tr.cpu().numpy() - g['tr'][t]).max() <= 1e-12, t
+        assert np.array_equal(goal[:, 0].cpu().numpy(), g['flags'][t]), t
+        assert np.abs(obs.cpu().numpy() - g['obs'][t]).max() <= 1e-12, t
+        assert np.abs(rew.cpu().numpy() - g['rew'][t]).max() <= 1e-12, t
+        assert np.array_equal(info['info_i'][:, :8].cpu().numpy(), g['info'][t]) and not done.any()
+
+
+def _near_threshold(pos, tr, eps):
+    """per env: does any collector-treasure / collector-collector / collector-deposit distance lie within eps of
+    its contact threshold, or do two treasure distances of one agent lie within eps of each other?"""
+    B = pos.shape[0]
+    near = np.zeros(B, dtype=bool)
+    c, d = pos[:, :6], pos[:, 6:]
+    dct = np.linalg.norm(c[:, :, None] - tr[:, None], axis=-1)
+    near |= (np.abs(dct - 0.075) < eps).any((1, 2))
+    dcc = np.linalg.norm(c[:, :, None] - c[:, None], axis=-1)
+    near |= (np.abs(dcc - 0.1) < eps).any((1, 2))
+    dcd = np.linalg.norm(c[:, :, None] - d[:, None], axis=-1)
+    near |= (np.abs(dcd - 0.125) < eps).any((1, 2))
+    dat = np.sort(np.linalg.norm(pos[:, :, None] - tr[:, None], axis=-1), axis=-1)
+    near |= (np.diff(dat, axis=-1) < eps).any((1, 2))
+    return near
+
+
+def test_fp32_build_one_step_from_every_fixture_state(golden_dir):
+    g = _gold(golden_dir)
+    T, B = g['act_u'].shape[:2]
+    env = _make(B, 'fp32', seed=int(g['seed']))
+    env.reset()
+    prev = (g['pos0'], g['vel0'], g['tr0'], g['flags0'])
+    checked = 0
+    for t in range(T):
+        _set(env, *prev)             # the fixture's float64 state, rounded to fp32 (step counter keeps running)
+        obs, rew, done, info = env.step(torch.from_numpy(g['act_u'][t].astype(np.int32)), info=True)
+        pos, vel, tr, goal = env.get_state()
+        ok = ~_near_threshold(g['pos'][t], prev[2], 1e-6)
+        # respawned treasures: positions are drawn in fp32 (u * 0.95f)
+        assert np.abs(pos.cpu().numpy() - g['pos'][t])[ok].max() <= 2e-6, t
+        assert np.abs(vel.cpu().numpy() - g['vel'][t])[ok].max() <= 2e-5, t
+        assert np.abs(tr.cpu().numpy() - g['tr'][t])[ok].max() <= 1e-4, t      # -999 and fresh draws
+        assert np.array_equal(goal[:, 0].cpu().numpy()[ok], g['flags'][t][ok]), t
+        o = obs.cpu().numpy()
+        far = np.abs(g['obs'][t]) > 100                                          # offsets to a dead treasure (~ -999)
+        assert np.abs(o - g['obs'][t])[ok][~far[ok]].max() <= 2e-6, t
+        assert np.abs(o - g['obs'][t])[ok][far[ok]].max() <= 1e-4, t
+        assert np.abs(rew.cpu().numpy() - g['rew'][t])[ok].max() <= 1e-5 + 1e-4 * far[ok].any(), t
+        assert np.array_equal(info['info_i'][:, :8].cpu().numpy()[ok], g['info'][t][ok])
+        checked += int(ok.sum())
+        prev = (g['pos'][t], g['vel'][t], g['tr'][t], g['flags'][t])
+    assert checked >= 0.97 * T * B
+
+
+@pytest.mark.parametrize('precision,B', [('fp64', 96), ('fp32', 129)])
+def test_long_run_against_the_loop_oracle(precision, B):
+    """Three 25-step episodes from the kernels' own Philox resets with random actions, ragged batch (partial warp):
+    the loop oracle is stepped env by env with the same draws.  fp32 is re-synchronised from the device state before
+    every step (single-step comparison); fp64 runs free."""
+    seed = 4242
+    env = _make(B, precision, seed=seed, env_id_offset=500)
+    rng = np.random.RandomState(5)
+    oracles = []
+    for b in range(B):
+        e = mpe_ref.make_env(SC)
+        e.scenario.draws = maac_ref.PhiloxDraws(seed, 500 + b)
+        oracles.append(e)
+    tol = 1e-12 if precision == 'fp64' else 3e-6
+    events = 0
+    for episode in range(3):
+        obs = env.reset().cpu().numpy()
+        for b, e in enumerate(oracles):
+            e.scenario.draws.episode = episode
+            o = e.reset()
+            assert np.abs(np.stack(o) - obs[b]).max() <= (0 if precision == 'fp64' else 3e-7)
+        for t in range(25):
+            act = rng.randint(0, 5, (B, 8)).astype(np.int32)
+            if precision == 'fp32':
+                pos, vel, tr, goal = (x.cpu().numpy() for x in env.get_state())
+            obs, rew, done, _ = env.step(torch.from_numpy(act))
+            obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+            f_dev = _flags(env)
+            for b, e in enumerate(oracles):
+                e.scenario.draws.tstep = t
+                if precision == 'fp32':
+                    maac_ref.set_state(e, pos[b], vel[b], tr[b], goal[b, 0])
+                f0 = maac_ref.get_flags(e)
+                o, r, _, _ = e.step([np.eye(5)[k] for k in act[b]])
+                events += int(maac_ref.get_flags(e) != f0)
+                if precision == 'fp32' and _near_threshold(np.stack([a.state.p_pos for a in e.world.agents])[None],
+                                                           tr[b][None], 1e-6)[0]:
+                    continue
+                far = np.abs(np.stack(o)) > 100
+                assert np.abs(np.stack(o) - obs[b])[~far].max() <= tol, (episode, t, b)
+                assert np.abs(np.array(r) - rew[b]).max() <= (tol if precision == 'fp64' else 2e-5 + 1e-4 * far.any())
+                assert maac_ref.get_flags(e) == f_dev[b], (episode, t, b)
+    assert events > 0
+
+
+def test_tracked_returns_and_auto_reset():
+    """rollout-style use: step + auto-reset after max_episode_len steps, episode statistics folded on the device."""
+    B = 300
+    env = _make(B, seed=9, max_episode_len=25)
+    env.track_returns(True)
+    obs = env.reset()
+    tot = torch.zeros(B, dtype=torch.float64, device=obs.device)
+    g = torch.Generator(device='cpu').manual_seed(0)
+    for t in range(25):
+        act = torch.randint(0, 5, (B, 8), generator=g, dtype=torch.int32)
+        obs, rew, done, _ = env.step(act)
+        tot += rew.double().sum(1)
+    env.reset()
+    st = env.read_stats()
+    assert st[2] == B and st[3] == 25 * B and st[4] == 0
+    assert abs(st[0] - float(tot.sum())) <= 1e-3 * B
+
+
+def test_rollout_with_the_actor_kernels():
+    """mpe_rollout for the 8-agent team: tensor-core actor (k_tc2<N = 8>) + step kernel per step; bit-identical to the
+    stepwise calls, logits of the actor within 1e-5 of the float64 restatement, both actor paths agree."""
+    import multiagent_rl_b200 as m
+    B, T = 700, 30
+    sd = actor_ref.init_state_dict(30, 5, 21)
+    envs = [_make(B, seed=3, max_episode_len=25) for _ in range(2)]
+    actor = m.FusedActor(sd, seed=3)
+    obs = envs[0].reset()
+    out = actor.forward(obs, want_logits=True)
+    want = actor_ref.forward(sd, obs.cpu().numpy())['logits'][0]
+    assert np.abs(out['logits'].cpu().numpy() - want).max() < 1e-5
+    simt = m.FusedActor(sd, seed=3, impl='simt').forward(obs, want_logits=True)
+    assert np.abs(simt['logits'].cpu().numpy() - want).max() < 1e-5
+    rec = envs[0].rollout(actor, T, step0=0, record=True)
+    obs = envs[1].reset()
+    for t in range(T):
+        a = actor.forward(obs, step=t)
+        assert torch.equal(a['act_u'], rec[2][t]), t
+        obs, rew, _, _ = envs[1].step(a['act_u'])
+        assert torch.equal(obs, rec[0][t]) and torch.equal(rew, rec[1][t]), t
+        if (t + 1) % 25 == 0:
+            obs = envs[1].reset()
+    assert torch.isfinite(rec[0]).all() and rec[1].abs().max() < 200
+
+
+def test_full_size_properties():
+    """1,048,576 envs x 50 steps with random actions: size-independent invariants of the scenario -
+    max_speed holds, positions of alive treasures stay inside the respawn box, a dead treasure sits at -999 for
+    exactly one step, holders hold an existing type, the observation's treasure list is sorted, rewards are finite."""
+    B = 1 << 20
+    env = _make(B, seed=5)
+    obs = env.reset()
+    g = torch.Generator(device='cuda').manual_seed(1)
+    dead_prev = torch.zeros(B, 6, dtype=torch.bool, device='cuda')
+    picked = 0
+    for t in range(50):
+        act = torch.randint(0, 5, (B, 8), generator=g, device='cuda', dtype=torch.int32)
+        obs, rew, done, _ = env.step(act)
+        pos, vel, tr, goal = env.get_state()
+        assert float(vel.norm(dim=-1).max()) <= 1.0 + 1e-6
+        f = goal[:, 0]
+        alive = ((f[:, None] >> (6 + torch.arange(6, device='cuda'))) & 1).bool()
+        assert bool(((tr.abs().amax(-1) < 0.95) == alive).all()) and bool((tr[~alive] == -999).all())
+        assert not bool((dead_prev & ~alive).any())      # respawn_prob = 1: back after one step
+        dead_prev = ~alive
+        hold = (f[:, None] >> (12 + 2 * torch.arange(6, device='cuda'))) & 3
+        assert int(hold.max()) <= 2 and int(f.max()) < (1 << 24)
+        picked += int((~alive).sum())
+        off = obs[:, :, 6:].reshape(B, 8, 6, 4)[..., :2]
+        d2 = (off.double() ** 2).sum(-1)
+        assert bool((d2[..., 1:] >= d2[..., :-1] * (1 - 1e-6)).all())
+        assert bool(torch.isfinite(rew).all())
+    assert picked > 1000
+
+
+@pytest.mark.skipif(not build_ref.available(), reason='oracle/_ref not built (python -m oracle.build_ref)')
+def test_reference_make_env_and_run_loop_on_the_cuda_env(tmp_path, monkeypatch):
+    """The reference's own make_env('fullobs_collect_treasure') (experiments/scenarios.py:124-192) on the multiagent
+    SHIM builds the CUDA env; its run loop (experiments/run.py:11-103) then drives it for two episodes with the fused
+    acting mixin.  Every stored transition is replayed through the float64 oracle: state from the observation rows
+    (own position / velocity / holding flags; treasure offsets of agent 0), one oracle step, same next observation
+    and summed reward."""
+    from tests import _refloop
+    import multiagent_rl_b200 as m
+    scen, run_mod, arglist = _refloop.use_reference('cuda')
+    saved = {k: getattr(arglist, k) for k in dir(arglist) if not k.startswith('_')}
+    monkeypatch.chdir(tmp_path)
+    os.makedirs(os.path.join('Models', arglist.appx))
+    keep = []
+    try:
+        from rls.agent.multiagent.ddpg_gumbel_fix import Trainer as RefTrainer
+
+        class Trainer(m.FusedActingMixin, RefTrainer):
+            def __init__(self, *a, **kw):
+                super(Trainer, self).__init__(*a, **kw)
+                keep.append(self)
+
+        env = scen.make_env(SC, benchmark=False, discrete_action=True, local_observation=True)
+        assert isinstance(env, m.BatchedMultiAgentEnv) and env.n == 8 and env.shared_reward is False
+        actor, critic, action_type = _refloop.main_py_setup(env, 12345678)
+        assert action_type == 'Discrete' and actor.dense1.module.weight.shape == (64, 30)
+        arglist.num_episodes, arglist.warmup_steps, arglist.save_rate = 2, 10 ** 9, 1
+        run_mod.run(env, actor, critic, Trainer, SC, action_type, cnt=0)
+    finally:
+        for k, v in saved.items():
+            setattr(arglist, k, v)
+        _refloop.purge()
+    mem = keep[0].memory
+    assert len(mem) == 50
+    ora = mpe_ref.make_env(SC)
+    for k, (obs_n, action_n, rew_shared, new_obs_n, done) in enumerate(mem._storage):
+        o = np.stack(obs_n)
+        pos, vel = o[:, 0:2], o[:, 2:4]
+        hold = [int(np.argmax(o[i, 4:6])) if o[i, 4:6].any() else -1 for i in range(6)]
+        lst = o[0, 6:].reshape(6, 4)
+        tr = lst[:, :2] + pos[0]
+        alive = [bool(x > -900) for x in tr[:, 0]]
+        tr[~np.array(alive)] = -999.0
+        types = [int(np.argmax(x)) for x in lst[:, 2:]]
+        maac_ref.set_state(ora, pos, vel, tr, maac_ref.pack_flags(types, alive, hold))
+        o2, r2, _, _ = ora.step([np.array(a, dtype=np.float64) for a in action_n])
+        far = np.abs(np.stack(o2)) > 100
+        assert np.abs(np.stack(o2) - np.stack(new_obs_n))[~far].max() <= 5e-6, k
+        assert abs(np.sum(r2) - rew_shared) <= 1e-3, k

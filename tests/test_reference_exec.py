@@ -99,9 +99,11 @@ def test_reference_make_env_reset_uses_numpy_global_rng_in_upstream_order(ref_sc
 
 
 def test_reference_unsupported_scenario_prints_but_does_not_patch(ref_scenarios, capsys):
-    """scenarios.py:151-164: the MAAC-fork names fall through to scenarios.load, which has no such script here."""
+    """scenarios.py:151-164: multi_speaker_listener falls through to scenarios.load, which has no such script here
+    (the reference leaves its stock, ragged observation in place - 'origin' - so its own actor cannot run it;
+    fullobs_collect_treasure is covered in tests/test_treasure_oracle.py)."""
     with pytest.raises(ImportError):
-        ref_scenarios.make_env('fullobs_collect_treasure')
+        ref_scenarios.make_env('multi_speaker_listener')
 
 
 def test_reference_replay_buffer_equals_restatement():
