@@ -12,8 +12,12 @@
 //   bit l        type of treasure l (two types = the two deposits)
 //   bit 6 + l    treasure l is alive (a collected treasure sits at (-999, -999) until it respawns one step later)
 //   bits 12+2i   what collector i holds: 0 = nothing, 1 + type otherwise
-// Observation rows are staged two agents at a time in shared memory (row stride 61: conflict-free scalar stores at
-// the rank-dependent offsets of the sorted treasure list) and leave as coalesced 128 B warp stores.
+// Output path (the first version spent half of its 9.5 k warp instructions per step in a cooperative copy loop with an
+// integer division per element, ncu: profiles/r2_ncu_treasure.txt): observation rows are staged two agents at a time
+// in a double-buffered shared-memory tile, written with 8 B stores at the rank-dependent offsets of the sorted treasure
+// list (row stride 68 values: 16 B aligned for the TMA engine, two-way conflicts at most), and every lane hands its own
+// env's 2 x 30 values to the TMA engine (cp.async.bulk, 240 B); rewards are one 32 B sector per lane.  The body has no
+// divergent region: lanes beyond the batch work on the last env and only their stores are predicated off.
 #pragma once
 #include "env_core.cuh"
 
@@ -21,12 +25,12 @@ namespace mpe {
 
 constexpr int kTrN = 8, kTrC = 6, kTrL = 6, kTrD = 30, kTrR = kTrN * kTrD;
 constexpr int kTrChunk = 2 * kTrD;      // two agents' rows per flush
-constexpr int kTrStride = kTrChunk + 1;  // odd shared-memory row stride
+constexpr int kTrStride = kTrChunk + 8;  // shared-memory row stride (values): 16 B multiple, 2-way conflicts for 8 B stores
 
 template <typename T>
 struct TrLayout {
-  static constexpr int kObsElems = 32 * kTrStride;
-  static constexpr int kWarpBytes = ((kObsElems + 32 * kTrN) * (int)sizeof(T) + 127) / 128 * 128;
+  static constexpr int kBufElems = 32 * kTrStride;
+  static constexpr int kWarpBytes = (2 * kBufElems * (int)sizeof(T) + 127) / 128 * 128;  // two buffers
   static constexpr int kBlockBytes = kWarpBytes * (kStepThreads / 32);
 };
 
@@ -125,17 +129,31 @@ struct TreasureEnv {
     }
 #pragma unroll
     for (int i = 0; i < kTrN; ++i) {
-      if (collector(i)) {
+      if constexpr (std::is_same<T, float>::value) {
+        // fp32: v = 0.75 v + (f / m) dt; the max_speed clip scales by max_speed * rsqrt(|v|^2) (MUFU, 2 ulp) instead of
+        // dividing by an IEEE square root
+        const float im = collector(i) ? 0.1f : (float)(0.1 / 2.25);
+        float vxi = fmaf(fx[i], im, vx[i] * 0.75f), vyi = fmaf(fy[i], im, vy[i] * 0.75f);
+        if (s.max_speed >= 0.0f) {
+          const float s2 = fmaf(vxi, vxi, vyi * vyi);
+          float rs;
+          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s2));
+          const float sc = s2 > s.max_speed * s.max_speed ? s.max_speed * rs : 1.0f;
+          vxi *= sc; vyi *= sc;
+        }
+        vx[i] = vxi; vy[i] = vyi;
+        px[i] = fmaf(vxi, 0.1f, px[i]);
+        py[i] = fmaf(vyi, 0.1f, py[i]);
+      } else if (collector(i)) {
         integrate_agent<T>(px[i], py[i], vx[i], vy[i], fx[i], fy[i], s.max_speed);
-      } else if (std::is_same<T, float>::value) {
-        integrate_agent<T>(px[i], py[i], vx[i], vy[i], fx[i] * (T)(1.0 / 2.25), fy[i] * (T)(1.0 / 2.25), s.max_speed);
       } else {
         integrate_agent<T>(px[i], py[i], vx[i], vy[i], fx[i] / (T)2.25, fy[i] / (T)2.25, s.max_speed);
       }
     }
   }
 
-  // Observation of agent i -> row[0..30); key[l] = distance (fp64 build) or squared distance (fp32) to treasure l
+  // Observation of agent i -> row[0..30) (8 B aligned); key[l] = distance (fp64 build) or squared distance (fp32)
+  // to treasure l
   __device__ __forceinline__ void obs_row(int i, T *row, T (&key)[kTrL]) const {
     T dxl[kTrL], dyl[kTrL];
     int rank[kTrL];
@@ -145,48 +163,61 @@ struct TreasureEnv {
       dyl[l] = ty[l] - py[i];
       const T d2 = sq2<T>(dxl[l], dyl[l]);
       key[l] = std::is_same<T, float>::value ? d2 : sqrt(d2);  // sorted(zip(cached_dist_mag, index)): ties by index
-      rank[l] = 0;
+      rank[l] = l;
     }
+    // rank[m] = m + #{n > m: key[m] > key[n]} - #{l < m: key[l] > key[m]}
 #pragma unroll
     for (int l = 0; l < kTrL; ++l)
 #pragma unroll
       for (int m = l + 1; m < kTrL; ++m) {
-        const bool gt = key[l] > key[m];
-        rank[l] += gt ? 1 : 0;
-        rank[m] += gt ? 0 : 1;
+        const int gt = key[l] > key[m] ? 1 : 0;
+        rank[l] += gt;
+        rank[m] -= gt;
       }
     const int h = collector(i) ? tr_hold(flags, i) : -1;
-    row[0] = px[i]; row[1] = py[i]; row[2] = vx[i]; row[3] = vy[i];
-    row[4] = h == 0 ? (T)1 : (T)0;
-    row[5] = h == 1 ? (T)1 : (T)0;
+    st2(row, Vec2<T>{px[i], py[i]});
+    st2(row + 2, Vec2<T>{vx[i], vy[i]});
+    st2(row + 4, Vec2<T>{h == 0 ? (T)1 : (T)0, h == 1 ? (T)1 : (T)0});
 #pragma unroll
     for (int l = 0; l < kTrL; ++l) {
       T *dst = row + 6 + 4 * rank[l];
-      const int ty_ = tr_type(flags, l);
-      dst[0] = dxl[l]; dst[1] = dyl[l];
-      dst[2] = ty_ == 0 ? (T)1 : (T)0;
-      dst[3] = ty_ == 1 ? (T)1 : (T)0;
+      const bool t1 = tr_type(flags, l) != 0;
+      st2(dst, Vec2<T>{dxl[l], dyl[l]});
+      st2(dst + 2, Vec2<T>{t1 ? (T)0 : (T)1, t1 ? (T)1 : (T)0});
     }
   }
 };
 
-// Observation rows of the warp's envs -> obs[b][8][30]; also returns, for the collectors of this thread's env, the
-// collector-treasure contact bits (bit i * 6 + l) and the distance key of the nearest treasure.
 template <typename T>
-__device__ __forceinline__ void tr_emit_obs(const TreasureEnv<T> &e, const EnvState<T> &s, T *obs, int64_t b0, int lane,
-                                            bool full, bool active, T *st_obs, uint64_t &ct, T (&near)[kTrC]) {
+__device__ __forceinline__ T tr_sqrt(T x) {
+  if constexpr (std::is_same<T, float>::value) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  } else {
+    return sqrt(x);
+  }
+}
+
+// Observation rows of this lane's env -> obs[b][8][30] through the warp's two staging buffers; also returns, for the
+// collectors of the env, the collector-treasure contact bits (bit i * 6 + l) and the distance key of the nearest
+// treasure.  `write`: this lane's env exists and obs is wanted.  Returns whether this lane issued bulk stores.
+template <typename T>
+__device__ __forceinline__ bool tr_emit_obs(const TreasureEnv<T> &e, const EnvState<T> &s, T *obs, int64_t b, int lane,
+                                            bool write, T *st_obs, uint64_t &ct, T (&near)[kTrC]) {
+  using TL = TrLayout<T>;
   ct = 0ull;
-  const bool staged = full && obs != nullptr;
+  const bool tma = write && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+  bool issued = false;
 #pragma unroll
   for (int c = 0; c < kTrN / 2; ++c) {
+    T *buf = st_obs + (c & 1) * TL::kBufElems + lane * kTrStride;
+    if (c >= 2) bulk_wait_read_1();  // the bulk store that read this buffer two chunks ago has drained it
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int i = 2 * c + k;
       T key[kTrL];
-      // partial warps write their rows straight to global memory; lanes without a row to write use the staging
-      // buffer as a sink (the distance keys are needed either way)
-      T *row = (staged || obs == nullptr || !active) ? st_obs + lane * kTrStride + k * kTrD : obs + (b0 + lane) * kTrR + i * kTrD;
-      e.obs_row(i, row, key);
+      e.obs_row(i, buf + k * kTrD, key);
       if (i < kTrC) {
         T m = key[0];
 #pragma unroll
@@ -198,16 +229,18 @@ __device__ __forceinline__ void tr_emit_obs(const TreasureEnv<T> &e, const EnvSt
         near[i] = m;
       }
     }
-    if (staged) {
-      __syncwarp();
-      T *dst = obs + b0 * kTrR + c * kTrChunk;
-      for (int idx = lane; idx < 32 * kTrChunk; idx += 32) {
-        const int env = idx / kTrChunk, j = idx - env * kTrChunk;
-        dst[(int64_t)env * kTrR + j] = st_obs[env * kTrStride + j];
-      }
-      __syncwarp();
+    T *dst = obs + b * kTrR + c * kTrChunk;
+    if (tma) {  // this lane's 2 x 30 values: 240 B (fp32), 16 B aligned on both sides
+      fence_proxy_async_smem();
+      bulk_store(dst, buf, kTrChunk * sizeof(T));
+      bulk_commit();
+      issued = true;
+    } else if (write) {  // caller's tensor is not 16 B aligned: plain stores
+#pragma unroll 4
+      for (int j = 0; j < kTrChunk; ++j) dst[j] = buf[j];
     }
   }
+  return issued;
 }
 
 // MODE 0: env.step   1: env.reset (masked / timed-out envs) + observation   2: observation only
@@ -218,167 +251,167 @@ __global__ void __launch_bounds__(kStepThreads)
   extern __shared__ __align__(128) unsigned char smem[];
   using TL = TrLayout<T>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t b0 = (int64_t)blockIdx.x * kStepThreads + warp * 32;
-  const int64_t b = b0 + lane;
-  const bool active = b < s.B;
-  const bool full = b0 + 32 <= s.B;
+  const int64_t b_raw = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+  const bool active = b_raw < s.B;
+  const int64_t b = active ? b_raw : s.B - 1;  // lanes beyond the batch shadow the last env; their stores are predicated off
   T *st_obs = reinterpret_cast<T *>(smem + warp * TL::kWarpBytes);
-  T *st_rew = st_obs + TL::kObsElems;
   TreasureEnv<T> e;
   uint32_t ep = 0;
   int tstep = 0;
   if (MODE == 1) {
     double ret = 0.0, n_ep = 0.0, n_steps = 0.0;
-    bool doit = false;
-    if (active) {
-      doit = (mask == nullptr || mask[b] != 0) && (auto_len <= 0 || s.tstep[b] >= auto_len);
-      if (doit) {
-        ep = s.episode[b] + 1u;
+    const int t_old = s.tstep[b];
+    const bool doit = (mask == nullptr || mask[b] != 0) && (auto_len <= 0 || t_old >= auto_len);
+    if (doit) {
+      ep = s.episode[b] + 1u;
+      e.reset(s.seed, (uint64_t)(s.gid0 + b), ep);
+      if (active) {
         s.episode[b] = ep;
-        e.reset(s.seed, (uint64_t)(s.gid0 + b), ep);
         e.store_agents(s, b);
         e.store_treasures(s, b, 0x3Fu);
-        const int t = s.tstep[b];
-        if (s.track && t > 0) { ret = (double)s.ep_ret[b]; n_ep = 1.0; n_steps = (double)t; }
+        if (s.track && t_old > 0) { ret = (double)s.ep_ret[b]; n_ep = 1.0; n_steps = (double)t_old; }
         s.tstep[b] = 0;
         s.ep_ret[b] = (T)0;
-      } else if (obs != nullptr) {
-        e.load(s, b);
       }
+    } else {
+      e.load(s, b);
     }
     if (s.track) fold_stats(s.stats, ret, n_ep, n_steps);
-  } else if (active) {
+    if (obs == nullptr) return;
+  } else {
     e.load(s, b);
   }
-  if (MODE == 0 && active) {
+  if (MODE == 0) {
     int au[kTrN];
+    if ((reinterpret_cast<uintptr_t>(act_u) & 15) == 0) {  // the usual case: two 16 B loads per env
+      const int4 a0 = *reinterpret_cast<const int4 *>(act_u + b * kTrN), a1 = *reinterpret_cast<const int4 *>(act_u + b * kTrN + 4);
+      au[0] = a0.x; au[1] = a0.y; au[2] = a0.z; au[3] = a0.w; au[4] = a1.x; au[5] = a1.y; au[6] = a1.z; au[7] = a1.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < kTrN; ++i) au[i] = act_u[b * kTrN + i];
+      for (int i = 0; i < kTrN; ++i) au[i] = act_u[b * kTrN + i];
+    }
     e.physics(au, s);
-    e.store_agents(s, b);
+    if (active) e.store_agents(s, b);
     ep = s.episode[b];
     tstep = s.tstep[b];
   }
   uint64_t ct;
   T near[kTrC];
-  if (MODE != 0 && obs == nullptr) return;
-  tr_emit_obs<T>(e, s, obs, b0, lane, full, active, st_obs, ct, near);
-  if (MODE != 0) return;
+  const bool issued = tr_emit_obs<T>(e, s, obs, b, lane, active && obs != nullptr, st_obs, ct, near);
+  if (MODE != 0) {
+    if (issued) bulk_wait_read_all();
+    return;
+  }
 
   // ---- rewards (taken BEFORE post_step) ----
   T r[kTrN];
   int bench[kTrN];
-  uint32_t moved = 0u;
-  if (active) {
-    const uint32_t f = e.flags;
-    int hold[kTrC];
+  const uint32_t f = e.flags;
+  int hold[kTrC];
 #pragma unroll
-    for (int i = 0; i < kTrC; ++i) hold[i] = tr_hold(f, i);
-    // collector-collector contacts, collector-deposit distances
-    int ncc[kTrC];
+  for (int i = 0; i < kTrC; ++i) hold[i] = tr_hold(f, i);
+  int ncc[kTrC];
 #pragma unroll
-    for (int i = 0; i < kTrC; ++i) ncc[i] = 0;
+  for (int i = 0; i < kTrC; ++i) ncc[i] = 0;
 #pragma unroll
-    for (int i = 0; i < kTrC; ++i)
+  for (int i = 0; i < kTrC; ++i)
 #pragma unroll
-      for (int j = i + 1; j < kTrC; ++j) {
-        const T d2 = sq2<T>(e.px[i] - e.px[j], e.py[i] - e.py[j]);
-        const bool hit = d2 < s.tr_t2[0];
-        ncc[i] += hit ? 1 : 0;
-        ncc[j] += hit ? 1 : 0;
-      }
-    T dcd[kTrC][2];   // distance collector i - deposit d
-    uint32_t cd = 0u;  // bit i * 2 + d: in contact
+    for (int j = i + 1; j < kTrC; ++j) {
+      const T d2 = sq2<T>(e.px[i] - e.px[j], e.py[i] - e.py[j]);
+      const int hit = d2 < s.tr_t2[0] ? 1 : 0;
+      ncc[i] += hit;
+      ncc[j] += hit;
+    }
+  T d2cd[kTrC][2];   // squared distance collector i - deposit d
+  uint32_t cd = 0u;  // bit i * 2 + d: in contact
 #pragma unroll
-    for (int i = 0; i < kTrC; ++i)
-#pragma unroll
-      for (int d = 0; d < 2; ++d) {
-        const T d2 = sq2<T>(e.px[i] - e.px[kTrC + d], e.py[i] - e.py[kTrC + d]);
-        dcd[i][d] = sqrt(d2);
-        cd |= (d2 < s.tr_t2[1]) ? (1u << (i * 2 + d)) : 0u;
-      }
-    int g_dep = 0, g_col = 0;
+  for (int i = 0; i < kTrC; ++i)
 #pragma unroll
     for (int d = 0; d < 2; ++d) {
-      int n = 0;
-#pragma unroll
-      for (int i = 0; i < kTrC; ++i) n += (hold[i] == d && ((cd >> (i * 2 + d)) & 1u)) ? 1 : 0;
-      g_dep += 5 * n;
+      d2cd[i][d] = sq2<T>(e.px[i] - e.px[kTrC + d], e.py[i] - e.py[kTrC + d]);
+      cd |= (d2cd[i][d] < s.tr_t2[1]) ? (1u << (i * 2 + d)) : 0u;
     }
+  int g_dep = 0, g_col = 0;
 #pragma unroll
-    for (int l = 0; l < kTrL; ++l) {
-      int n = 0;
+  for (int i = 0; i < kTrC; ++i) {
+    const bool none = hold[i] < 0;
+    g_dep += (!none && ((cd >> (i * 2 + (hold[i] > 0 ? 1 : 0))) & 1u)) ? 5 : 0;
+    g_col += none ? 5 * __popc((uint32_t)(ct >> (i * 6)) & 0x3Fu) : 0;
+  }
+  const T glob = (T)(g_dep + g_col);
 #pragma unroll
-      for (int i = 0; i < kTrC; ++i) n += (hold[i] < 0 && ((ct >> (i * 6 + l)) & 1ull)) ? 1 : 0;
-      g_col += 5 * n;
-    }
-    const T glob = (T)(g_dep + g_col);
+  for (int i = 0; i < kTrC; ++i) {
+    // nearest treasure while holding nothing, else the deposit of the held type (sqrt is monotone: min of squares)
+    const T key = hold[i] < 0 ? near[i] : (hold[i] == 0 ? d2cd[i][0] : d2cd[i][1]);
+    const T shaped = (std::is_same<T, float>::value || hold[i] >= 0) ? tr_sqrt<T>(key) : key;  // fp64: near[] is a distance
+    T rr = (T)(-5 * ncc[i]);
+    rr -= (T)0.1 * shaped;
+    r[i] = rr + glob;
+    const bool at_dep = hold[i] >= 0 && ((cd >> (i * 2 + (hold[i] > 0 ? 1 : 0))) & 1u);
+    const bool at_tr = hold[i] < 0 && ((ct >> (i * 6)) & 0x3Full) != 0ull;
+    bench[i] = (at_dep || at_tr) ? 1 : 0;
+  }
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    bool any = false;
+    T m2 = (T)0;
 #pragma unroll
     for (int i = 0; i < kTrC; ++i) {
-      const T nearest = std::is_same<T, float>::value ? sqrt(near[i]) : near[i];
-      const T shaped = hold[i] < 0 ? nearest : (hold[i] == 0 ? dcd[i][0] : dcd[i][1]);
-      T rr = (T)(-5 * ncc[i]);
-      rr -= (T)0.1 * shaped;
-      r[i] = rr + glob;
-      const bool at_dep = hold[i] >= 0 && ((cd >> (i * 2 + (hold[i] > 0 ? 1 : 0))) & 1u);
-      const bool at_tr = hold[i] < 0 && ((ct >> (i * 6)) & 0x3Full) != 0ull;
-      bench[i] = (at_dep || at_tr) ? 1 : 0;
+      const bool h = hold[i] == d;
+      m2 = h ? (any ? (d2cd[i][d] < m2 ? d2cd[i][d] : m2) : d2cd[i][d]) : m2;
+      any = any || h;
     }
+    // no holder of this type: mean offset of the seven other agents
+    T sx = (T)0, sy = (T)0;
 #pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      bool any = false;
-      T m = (T)0;
-#pragma unroll
-      for (int i = 0; i < kTrC; ++i)
-        if (hold[i] == d) { m = any ? (dcd[i][d] < m ? dcd[i][d] : m) : dcd[i][d]; any = true; }
-      if (!any) {  // mean offset of the seven other agents
-        T sx = (T)0, sy = (T)0;
-#pragma unroll
-        for (int j = 0; j < kTrN; ++j)
-          if (j != kTrC + d) { sx += e.px[j] - e.px[kTrC + d]; sy += e.py[j] - e.py[kTrC + d]; }
-        sx = sx / (T)7; sy = sy / (T)7;
-        m = sqrt(sq2<T>(sx, sy));
-      }
-      T rr = (T)0;
-      rr -= (T)0.1 * m;
-      r[kTrC + d] = rr + glob;
-      bench[kTrC + d] = 0;
-    }
+    for (int j = 0; j < kTrN; ++j)
+      if (j != kTrC + d) { sx += e.px[j] - e.px[kTrC + d]; sy += e.py[j] - e.py[kTrC + d]; }
+    sx = sx / (T)7; sy = sy / (T)7;
+    const T m = tr_sqrt<T>(any ? m2 : sq2<T>(sx, sy));
+    T rr = (T)0;
+    rr -= (T)0.1 * m;
+    r[kTrC + d] = rr + glob;
+    bench[kTrC + d] = 0;
+  }
 
-    // ---- Scenario.post_step: pick-up, respawn of the treasures collected one step earlier, deposit ----
-    uint32_t nf = f;
+  // ---- Scenario.post_step: pick-up, respawn of the treasures collected one step earlier, deposit ----
+  uint32_t nf = f, moved = 0u;
 #pragma unroll
-    for (int l = 0; l < kTrL; ++l) {
-      if (tr_alive(f, l)) {
-        bool taken = false;
-#pragma unroll
-        for (int i = 0; i < kTrC; ++i) {
-          const bool can = !taken && (((nf >> (12 + 2 * i)) & 3u) == 0u) && ((ct >> (i * 6 + l)) & 1ull);
-          if (can) {
-            taken = true;
-            nf |= (uint32_t)(1 + tr_type(f, l)) << (12 + 2 * i);
-          }
-        }
-        if (taken) {
-          nf &= ~(1u << (6 + l));
-          e.tx[l] = (T)-999; e.ty[l] = (T)-999;
-          moved |= 1u << l;
-        }
-      } else {
-        const uint4 q = philox_raw(s.seed, (uint64_t)(s.gid0 + b), ep, kDomainRespawn, ((uint32_t)(tstep & 0xFFF) << 4) | (uint32_t)l);
-        // respawn_prob = 1.0: the probability draw (q.w) always passes
-        e.tx[l] = bits_to_pos<T>(q.x) * (T)0.95;
-        e.ty[l] = bits_to_pos<T>(q.y) * (T)0.95;
-        nf = (nf & ~(1u << l)) | ((q.z >> 31) << l) | (1u << (6 + l));
-        moved |= 1u << l;
-      }
-    }
+  for (int l = 0; l < kTrL; ++l) {
+    bool taken = false;
 #pragma unroll
     for (int i = 0; i < kTrC; ++i) {
-      const int h = (int)((nf >> (12 + 2 * i)) & 3u) - 1;
-      if (h >= 0 && ((cd >> (i * 2 + (h > 0 ? 1 : 0))) & 1u)) nf &= ~(3u << (12 + 2 * i));
+      const bool can = !taken && (((nf >> (12 + 2 * i)) & 3u) == 0u) && ((ct >> (i * 6 + l)) & 1ull) && tr_alive(f, l);
+      nf |= can ? ((uint32_t)(1 + tr_type(f, l)) << (12 + 2 * i)) : 0u;
+      taken = taken || can;
     }
-    e.flags = nf;
+    if (taken) {
+      nf &= ~(1u << (6 + l));
+      e.tx[l] = (T)-999; e.ty[l] = (T)-999;
+      moved |= 1u << l;
+    }
+  }
+  uint32_t dead = ~(f >> 6) & 0x3Fu;  // collected one step earlier: respawn now (respawn_prob = 1.0: the draw always passes)
+  if (dead != 0u) {                    // rare
+#pragma unroll 1
+    for (int l = 0; l < kTrL; ++l) {
+      if (!((dead >> l) & 1u)) continue;
+      const uint4 q = philox_raw(s.seed, (uint64_t)(s.gid0 + b), ep, kDomainRespawn, ((uint32_t)(tstep & 0xFFF) << 4) | (uint32_t)l);
+      const T x = bits_to_pos<T>(q.x) * (T)0.95, y = bits_to_pos<T>(q.y) * (T)0.95;
+#pragma unroll
+      for (int k = 0; k < kTrL; ++k)
+        if (k == l) { e.tx[k] = x; e.ty[k] = y; }
+      nf = (nf & ~(1u << l)) | ((q.z >> 31) << l) | (1u << (6 + l));
+    }
+    moved |= dead;
+  }
+#pragma unroll
+  for (int i = 0; i < kTrC; ++i) {
+    const int h = (int)((nf >> (12 + 2 * i)) & 3u) - 1;
+    if (h >= 0 && ((cd >> (i * 2 + (h > 0 ? 1 : 0))) & 1u)) nf &= ~(3u << (12 + 2 * i));
+  }
+  e.flags = nf;
+  if (active) {
     e.store_treasures(s, b, moved);
     s.tstep[b] = tstep + 1;
     if (s.track) {
@@ -392,27 +425,25 @@ __global__ void __launch_bounds__(kStepThreads)
       for (int i = 0; i < kTrN; ++i) info_i[b * (kTrN + 1) + i] = bench[i];
       info_i[b * (kTrN + 1) + kTrN] = 0;
     }
-  }
-  if (done != nullptr) {
-    if (full) {
-      uint32_t *d32 = reinterpret_cast<uint32_t *>(done + b0 * kTrN);  // 256 bytes per warp
-      for (int k = lane; k < 8 * kTrN; k += 32) d32[k] = 0u;
-    } else if (active) {
+    if (done != nullptr) {  // no done_callback (experiments/scenarios.py:186-190): always False
+      if ((reinterpret_cast<uintptr_t>(done) & 7) == 0) {
+        *reinterpret_cast<uint2 *>(done + b * kTrN) = make_uint2(0u, 0u);
+      } else {
 #pragma unroll
-      for (int i = 0; i < kTrN; ++i) done[b * kTrN + i] = 0;
+        for (int i = 0; i < kTrN; ++i) done[b * kTrN + i] = 0;
+      }
+    }
+    if (rew != nullptr) {  // 8 rewards = one 32 B sector (fp32) per lane
+      if ((reinterpret_cast<uintptr_t>(rew) & 15) == 0) {
+        st4(rew + b * kTrN, Vec4<T>{r[0], r[1], r[2], r[3]});
+        st4(rew + b * kTrN + 4, Vec4<T>{r[4], r[5], r[6], r[7]});
+      } else {
+#pragma unroll
+        for (int i = 0; i < kTrN; ++i) rew[b * kTrN + i] = r[i];
+      }
     }
   }
-  if (rew != nullptr) {
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < kTrN; ++i) st_rew[lane * kTrN + i] = r[i];
-      __syncwarp();
-      for (int idx = lane; idx < 32 * kTrN; idx += 32) rew[b0 * kTrN + idx] = st_rew[idx];
-    } else if (active) {
-#pragma unroll
-      for (int i = 0; i < kTrN; ++i) rew[b * kTrN + i] = r[i];
-    }
-  }
+  if (issued) bulk_wait_read_all();
 }
 
 }  // namespace mpe

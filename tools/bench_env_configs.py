@@ -1,5 +1,6 @@
 """Env-only step kernel across BASELINE configs 2/3/4: us per launch, algorithmic GB/s, fraction of measured HBM
-peak.  bytes per env step = 41N + 8L + 4ND (+ second action index and comm state for simple_reference)."""
+peak.  bytes per env step = 41N + 8L + 4ND (+ second action index and comm state for simple_reference,
++ the state word of fullobs_collect_treasure)."""
 import json
 import os
 import sys
@@ -10,7 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiagent_rl_b200 as m  # noqa: E402
 
 CONFIGS = [('simple_spread', None, 1 << 20), ('simple_spread', 6, 1 << 19), ('simple_spread', 9, 1 << 18),
-           ('simple_spread', 12, 1 << 18), ('simple_reference', None, 1 << 20), ('simple_speaker_listener', None, 1 << 20)]
+           ('simple_spread', 12, 1 << 18), ('simple_reference', None, 1 << 20), ('simple_speaker_listener', None, 1 << 20),
+           ('fullobs_collect_treasure', None, 1 << 18)]
 
 
 def run(dev, peak, verbose=False, reps=30):
@@ -21,6 +23,8 @@ def run(dev, peak, verbose=False, reps=30):
         nbytes = 41 * N + 8 * L + 4 * N * D
         if scen == 'simple_reference':
             nbytes += 4 * N + 4 * N * 10
+        if scen == 'fullobs_collect_treasure':
+            nbytes += 8  # the per-env state word (types / alive / holding), read and written; treasure moves are rare
         env.reset()
         au = torch.randint(0, 5, (B, N), dtype=torch.int32, device=dev)
         ac = torch.randint(0, 10, (B, N), dtype=torch.int32, device=dev) if env.act_c else None

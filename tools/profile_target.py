@@ -73,4 +73,14 @@ if which == 'critic':
     for _ in range(2):
         am.forward(o6, want_next_state=True)
     torch.cuda.synchronize()
+if which == 'treasure':
+    B = 1 << 18
+    env = m.make_env('fullobs_collect_treasure', num_envs=B, batched=True, seed=1)
+    env.reset()
+    act = torch.randint(0, 5, (B, 8), dtype=torch.int32, device=dev)
+    outs = [(torch.empty((B, 8, 30), device=dev), torch.empty((B, 8), device=dev),
+             torch.empty((B, 8), dtype=torch.uint8, device=dev)) for _ in range(3)]
+    for i in range(6):
+        env.step(act, out=outs[i % 3])
+    torch.cuda.synchronize()
 print('profile target done')
