@@ -12,12 +12,12 @@
 //   bit l        type of treasure l (two types = the two deposits)
 //   bit 6 + l    treasure l is alive (a collected treasure sits at (-999, -999) until it respawns one step later)
 //   bits 12+2i   what collector i holds: 0 = nothing, 1 + type otherwise
-// Output path (the first version spent half of its 9.5 k warp instructions per step in a cooperative copy loop with an
-// integer division per element, ncu: profiles/r2_ncu_treasure.txt): observation rows are staged two agents at a time
-// in a double-buffered shared-memory tile, written with 8 B stores at the rank-dependent offsets of the sorted treasure
-// list (row stride 68 values: 16 B aligned for the TMA engine, two-way conflicts at most), and every lane hands its own
-// env's 2 x 30 values to the TMA engine (cp.async.bulk, 240 B); rewards are one 32 B sector per lane.  The body has no
-// divergent region: lanes beyond the batch work on the last env and only their stores are predicated off.
+// Output path: observation rows are staged two agents at a time in a per-warp shared-memory tile (row stride 68
+// values: the 16 B vectors of a row start in different bank groups), written with 8 B stores at the rank-dependent
+// offsets of the sorted treasure list, and leave as coalesced 16 B-per-lane warp stores; rewards are one 32 B sector
+// per lane.  The body has no divergent region: lanes beyond the batch work on the last env and only their stores are
+// predicated off.  (History, ncu in profiles/r2_ncu_treasure.txt: v1 spent half of its 9.5 k warp instructions per
+// step in a copy loop with an integer division per element; v2's per-lane cp.async.bulk was serialised over the lanes.)
 #pragma once
 #include "env_core.cuh"
 
@@ -26,11 +26,14 @@ namespace mpe {
 constexpr int kTrN = 8, kTrC = 6, kTrL = 6, kTrD = 30, kTrR = kTrN * kTrD;
 constexpr int kTrChunk = 2 * kTrD;      // two agents' rows per flush
 constexpr int kTrStride = kTrChunk + 8;  // shared-memory row stride (values): 16 B multiple, 2-way conflicts for 8 B stores
+#ifndef MPE_TR_MIN_BLOCKS
+#define MPE_TR_MIN_BLOCKS 3
+#endif
+constexpr int kTrMinBlocks = MPE_TR_MIN_BLOCKS;  // resident CTAs per SM the fp32 kernels are compiled for (register cap)
 
 template <typename T>
 struct TrLayout {
-  static constexpr int kBufElems = 32 * kTrStride;
-  static constexpr int kWarpBytes = (2 * kBufElems * (int)sizeof(T) + 127) / 128 * 128;  // two buffers
+  static constexpr int kWarpBytes = (32 * kTrStride * (int)sizeof(T) + 127) / 128 * 128;
   static constexpr int kBlockBytes = kWarpBytes * (kStepThreads / 32);
 };
 
@@ -154,7 +157,7 @@ struct TreasureEnv {
 
   // Observation of agent i -> row[0..30) (8 B aligned); key[l] = distance (fp64 build) or squared distance (fp32)
   // to treasure l
-  __device__ __forceinline__ void obs_row(int i, T *row, T (&key)[kTrL]) const {
+  __device__ __forceinline__ void obs_row(int i, T *row, T (&key)[kTrL], const Vec2<T> (&type1h)[kTrL]) const {
     T dxl[kTrL], dyl[kTrL];
     int rank[kTrL];
 #pragma unroll
@@ -181,9 +184,8 @@ struct TreasureEnv {
 #pragma unroll
     for (int l = 0; l < kTrL; ++l) {
       T *dst = row + 6 + 4 * rank[l];
-      const bool t1 = tr_type(flags, l) != 0;
       st2(dst, Vec2<T>{dxl[l], dyl[l]});
-      st2(dst + 2, Vec2<T>{t1 ? (T)0 : (T)1, t1 ? (T)1 : (T)0});
+      st2(dst + 2, type1h[l]);
     }
   }
 };
@@ -199,53 +201,76 @@ __device__ __forceinline__ T tr_sqrt(T x) {
   }
 }
 
-// Observation rows of this lane's env -> obs[b][8][30] through the warp's two staging buffers; also returns, for the
-// collectors of the env, the collector-treasure contact bits (bit i * 6 + l) and the distance key of the nearest
-// treasure.  `write`: this lane's env exists and obs is wanted.  Returns whether this lane issued bulk stores.
+// Observation rows of the warp's 32 envs -> obs[b][8][30], two agents at a time through the warp's staging tile; also
+// returns, for the collectors of this lane's env, the collector-treasure contact bits (ct[i] bit l) and the distance
+// key of the nearest treasure.  Copy-out of a tile (32 envs x 15 16 B vectors in fp32): round `it` moves envs 2 it and
+// 2 it + 1, lanes 0..14 the vectors of the first, lanes 15..29 those of the second, so that every address is a
+// per-lane base plus a compile-time offset (16 rounds of LDS.128 + STG.128 with immediate offsets, 30 of 32 lanes
+// busy; 240 B contiguous per env).  [A per-lane cp.async.bulk of each env's 240 B was measured first: UBLKCP takes
+// uniform operands, so the compiler serialises it over the 32 lanes - a third of the kernel's instructions; a copy
+// loop over vector index 32 it + lane spends more on its index arithmetic than on the copies.]
+// `n_valid`: envs of this warp that exist (32 except in the last warp).
 template <typename T>
-__device__ __forceinline__ bool tr_emit_obs(const TreasureEnv<T> &e, const EnvState<T> &s, T *obs, int64_t b, int lane,
-                                            bool write, T *st_obs, uint64_t &ct, T (&near)[kTrC]) {
-  using TL = TrLayout<T>;
-  ct = 0ull;
-  const bool tma = write && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
-  bool issued = false;
+__device__ __forceinline__ void tr_emit_obs(const TreasureEnv<T> &e, const EnvState<T> &s, T *obs, int64_t b0, int lane,
+                                            int n_valid, T *st_obs, uint32_t (&ct)[kTrC], T (&near)[kTrC]) {
+  constexpr int kVec = 16 / (int)sizeof(T);        // values per 16 B vector
+  constexpr int kPerEnv = kTrChunk / kVec;          // vectors per env and chunk (15 in fp32, 30 in fp64)
+  constexpr int kEnvsPerRound = 32 / kPerEnv;       // 2 (fp32), 1 (fp64)
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
+  Vec2<T> type1h[kTrL];
+#pragma unroll
+  for (int l = 0; l < kTrL; ++l) {
+    const bool t1 = tr_type(e.flags, l) != 0;
+    type1h[l] = Vec2<T>{t1 ? (T)0 : (T)1, t1 ? (T)1 : (T)0};
+  }
+  T *row = st_obs + lane * kTrStride;
+  // copy-out addressing of this lane: env (within a round) and vector slot
+  const int sub = lane / kPerEnv, slot = lane - sub * kPerEnv;
+  const bool mover = sub < kEnvsPerRound;
+  const T *src0 = st_obs + sub * kTrStride + slot * kVec;
+  T *dst0 = obs + (b0 + sub) * kTrR + slot * kVec;
 #pragma unroll
   for (int c = 0; c < kTrN / 2; ++c) {
-    T *buf = st_obs + (c & 1) * TL::kBufElems + lane * kTrStride;
-    if (c >= 2) bulk_wait_read_1();  // the bulk store that read this buffer two chunks ago has drained it
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int i = 2 * c + k;
       T key[kTrL];
-      e.obs_row(i, buf + k * kTrD, key);
+      e.obs_row(i, row + k * kTrD, key, type1h);
       if (i < kTrC) {
         T m = key[0];
+        uint32_t bits = 0u;
 #pragma unroll
         for (int l = 0; l < kTrL; ++l) {
           m = key[l] < m ? key[l] : m;
           const bool hit = std::is_same<T, float>::value ? key[l] < s.tr_t2[2] : key[l] < (T)(0.05 + 0.025);
-          ct |= hit ? (1ull << (i * 6 + l)) : 0ull;
+          bits |= hit ? (1u << l) : 0u;
         }
         near[i] = m;
+        ct[i] = bits;
       }
     }
-    T *dst = obs + b * kTrR + c * kTrChunk;
-    if (tma) {  // this lane's 2 x 30 values: 240 B (fp32), 16 B aligned on both sides
-      fence_proxy_async_smem();
-      bulk_store(dst, buf, kTrChunk * sizeof(T));
-      bulk_commit();
-      issued = true;
-    } else if (write) {  // caller's tensor is not 16 B aligned: plain stores
-#pragma unroll 4
-      for (int j = 0; j < kTrChunk; ++j) dst[j] = buf[j];
+    __syncwarp();
+    if (obs != nullptr) {
+      if (vec_ok && n_valid == 32) {
+        if (mover) {
+#pragma unroll
+          for (int it = 0; it < 32 / kEnvsPerRound; ++it) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(src0 + it * kEnvsPerRound * kTrStride);
+            *reinterpret_cast<uint4 *>(dst0 + (int64_t)it * kEnvsPerRound * kTrR + c * kTrChunk) = v;
+          }
+        }
+      } else if (lane < n_valid) {  // last warp of a ragged batch / unaligned tensor: scalar copy of the lane's own row
+        T *dst = obs + (b0 + lane) * kTrR + c * kTrChunk;
+        for (int jj = 0; jj < kTrChunk; ++jj) dst[jj] = row[jj];
+      }
     }
+    __syncwarp();
   }
-  return issued;
 }
 
 // MODE 0: env.step   1: env.reset (masked / timed-out envs) + observation   2: observation only
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kStepThreads)
+__global__ void __launch_bounds__(kStepThreads, std::is_same<T, float>::value ? kTrMinBlocks : 1)
     k_treasure(EnvState<T> s, const int32_t *__restrict__ act_u, const uint8_t *__restrict__ mask, int auto_len,
                T *__restrict__ obs, T *__restrict__ rew, uint8_t *__restrict__ done, int32_t *__restrict__ info_i) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -290,18 +315,17 @@ __global__ void __launch_bounds__(kStepThreads)
 #pragma unroll
       for (int i = 0; i < kTrN; ++i) au[i] = act_u[b * kTrN + i];
     }
+    ep = s.episode[b];  // requested before the stores below (no aliasing information: they would be ordered after them)
+    tstep = s.tstep[b];
     e.physics(au, s);
     if (active) e.store_agents(s, b);
-    ep = s.episode[b];
-    tstep = s.tstep[b];
   }
-  uint64_t ct;
+  uint32_t ct[kTrC];  // collector i touches treasure l: bit l
   T near[kTrC];
-  const bool issued = tr_emit_obs<T>(e, s, obs, b, lane, active && obs != nullptr, st_obs, ct, near);
-  if (MODE != 0) {
-    if (issued) bulk_wait_read_all();
-    return;
-  }
+  const int64_t b0 = b_raw - lane;
+  const int n_valid = (int)((s.B - b0) < 32 ? (s.B - b0) : 32);
+  tr_emit_obs<T>(e, s, obs, b0, lane, n_valid, st_obs, ct, near);
+  if (MODE != 0) return;
 
   // ---- rewards (taken BEFORE post_step) ----
   T r[kTrN];
@@ -336,7 +360,7 @@ __global__ void __launch_bounds__(kStepThreads)
   for (int i = 0; i < kTrC; ++i) {
     const bool none = hold[i] < 0;
     g_dep += (!none && ((cd >> (i * 2 + (hold[i] > 0 ? 1 : 0))) & 1u)) ? 5 : 0;
-    g_col += none ? 5 * __popc((uint32_t)(ct >> (i * 6)) & 0x3Fu) : 0;
+    g_col += none ? 5 * __popc(ct[i]) : 0;
   }
   const T glob = (T)(g_dep + g_col);
 #pragma unroll
@@ -348,7 +372,7 @@ __global__ void __launch_bounds__(kStepThreads)
     rr -= (T)0.1 * shaped;
     r[i] = rr + glob;
     const bool at_dep = hold[i] >= 0 && ((cd >> (i * 2 + (hold[i] > 0 ? 1 : 0))) & 1u);
-    const bool at_tr = hold[i] < 0 && ((ct >> (i * 6)) & 0x3Full) != 0ull;
+    const bool at_tr = hold[i] < 0 && ct[i] != 0u;
     bench[i] = (at_dep || at_tr) ? 1 : 0;
   }
 #pragma unroll
@@ -381,7 +405,7 @@ __global__ void __launch_bounds__(kStepThreads)
     bool taken = false;
 #pragma unroll
     for (int i = 0; i < kTrC; ++i) {
-      const bool can = !taken && (((nf >> (12 + 2 * i)) & 3u) == 0u) && ((ct >> (i * 6 + l)) & 1ull) && tr_alive(f, l);
+      const bool can = !taken && (((nf >> (12 + 2 * i)) & 3u) == 0u) && ((ct[i] >> l) & 1u) && tr_alive(f, l);
       nf |= can ? ((uint32_t)(1 + tr_type(f, l)) << (12 + 2 * i)) : 0u;
       taken = taken || can;
     }
@@ -443,7 +467,6 @@ __global__ void __launch_bounds__(kStepThreads)
       }
     }
   }
-  if (issued) bulk_wait_read_all();
 }
 
 }  // namespace mpe
