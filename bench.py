@@ -544,6 +544,37 @@ def side_measurements(m, actor, dev, pk, off):
                                  'tflops': B * FLOPS_PER_ENV_STEP / s / 1e12,
                                  'frac_of_bf16_sustained': B * FLOPS_PER_ENV_STEP / s / 1e12 / pk['bf16_tflops_sustained']}
     del env
+    # The headline step again with INPUTS LARGER THAN L2 instead of a flush: 16 independent shards of 65,536 envs
+    # (16 x 17.5 MB of state + outputs = 280 MB > 126 MB) stepped round-robin, one launch per step, per-step event
+    # pairs.  Every launch finds its data cold in L2 but the kernel's code and the 106 KB weight image warm - what a
+    # rollout loop sees - so the difference to `value` is what the flush costs in instruction / weight refetch.
+    nsh, Bs = 16, 65536
+    shards = []
+    for k in range(nsh):
+        e = m.make_env(SCENARIO, num_envs=Bs, batched=True, seed=SEED, env_id_offset=k * Bs, max_episode_len=EP_LEN)
+        e.reset()
+        shards.append((e, torch.empty((1, Bs, N_AGENTS, OBS_DIM), device=dev), torch.empty((1, Bs, N_AGENTS), device=dev),
+                       torch.empty((1, Bs, N_AGENTS), dtype=torch.int32, device=dev)))
+
+    def fused_shard(k, t):
+        e, o, r, a = shards[k]
+        _lib.check(lib.mpe_rollout(e._h, actor._h, 1, t, _lib.ptr(o), _lib.ptr(r), _lib.ptr(a), None,
+                                   _lib.current_stream(dev)), 'mpe_rollout')
+    for i in range(2 * nsh):
+        fused_shard(i % nsh, i // nsh)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10 * nsh)]
+    for i, (a, b) in enumerate(evs):
+        a.record()
+        fused_shard(i % nsh, 2 + i // nsh)
+        b.record()
+    torch.cuda.synchronize()
+    per = sorted(a.elapsed_time(b) for a, b in evs)
+    s = sum(per) / len(per) * 1e-3
+    out['fused_step_rotating_shards'] = {'envs_per_launch': Bs, 'shards': nsh, 'ms_per_step': s * 1e3,
+                                         'p50_ms': per[len(per) // 2], 'agent_steps_per_s': Bs * N_AGENTS / s,
+                                         'l2': 'no flush: %d shards x 17.5 MB rotate (inputs larger than L2)' % nsh}
+    del shards
     sys.path.insert(0, os.path.join(ROOT, 'tools'))
     import bench_env_configs
     out['env_step_configs'] = bench_env_configs.run(dev, pk['hbm_gbs'])  # configs 3/4: env-only HBM fractions

@@ -83,7 +83,9 @@ int mpe_reset(MpeEnv *env, const uint8_t *mask, void *obs_out, void *stream);
 
 /* State injection / readback (parity tests; host-drawn resets that mirror upstream's
  * np.random order).  pos/vel [B][N][2] real, lm [B][L][2] real, goal [B][N] int32 (-1 = None);
- * any pointer may be NULL to skip it. */
+ * any pointer may be NULL to skip it.  MPE_COLLECT_TREASURE: lm = the six treasure positions and goal[b][0] = the
+ * env's state word (bit l: type of treasure l; bit 6 + l: alive; bits 12 + 2 i: what collector i holds, 0 = nothing,
+ * 1 + type otherwise); goal[b][1..] is ignored / left at -1. */
 int mpe_set_state(MpeEnv *env, const void *pos, const void *vel, const void *lm, const int32_t *goal,
                   void *stream);
 int mpe_get_state(MpeEnv *env, void *pos, void *vel, void *lm, int32_t *goal, void *stream);
@@ -100,7 +102,11 @@ int mpe_observe(MpeEnv *env, void *obs_out, void *stream);
  *   only read for scenarios with a talking agent);
  * obs [B][N][D] real, rew [B][N] real, done [B][N] uint8 (always 0: no done_callback,
  *   scenarios.py:186-190), info_i [B][N+1] int32 = benchmark_data collisions per agent +
- *   occupied landmarks, info_f [B] real = benchmark_data min_dists; each output may be NULL. */
+ *   occupied landmarks, info_f [B] real = benchmark_data min_dists; each output may be NULL.
+ * MPE_COLLECT_TREASURE (experiments/scenarios.py:95-121,174-190 + the MAAC fork's scenario): sensitivity = accel,
+ *   mass-aware contact forces, max_speed clip; observation / reward are taken BEFORE Scenario.post_step (pick-up,
+ *   respawn, deposit), which runs at the end of the same kernel; info_i [B][N+1] = benchmark_data per agent (0 / 1)
+ *   and a zero; info_f is not written. */
 int mpe_step(MpeEnv *env, const int32_t *act_u, const int32_t *act_c, const void *comm_vec, void *obs,
              void *rew, uint8_t *done, int32_t *info_i, void *info_f, void *stream);
 

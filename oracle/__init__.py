@@ -17,6 +17,9 @@ Parity status (see DESIGN.md "Oracle"):
     and are **pinned by execution**: ``python -m oracle.build_ref`` byte-compiles the reference's modules into
     ``oracle/_ref`` and tests/test_reference_exec.py runs the reference's own ``make_env`` against this package
     (bit-exact on all fixtures).
+  * MAAC-fork engine + ``fullobs_collect_treasure`` (``maac_ref``): **parity unpinned** for the fork-side arithmetic
+    (shariqiqbal2810/multiagent-particle-envs, not in the reference tree); its observation restates
+    /root/reference/experiments/scenarios.py:95-121 and is **pinned by execution** (tests/test_treasure_oracle.py).
   * actor forward (``actor_ref``): **pinned** against the reference's own
     ``rls.model.ac_network_multi_gumbel.ActorNetwork`` run in the authoring
     container (``oracle/gen_golden.py`` -> ``tests/golden/actor_*.npz``); critic forward (``critic_ref``) likewise

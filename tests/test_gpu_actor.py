@@ -241,7 +241,8 @@ def test_host_buffer_acting_matches_device_acting():
 
 
 @pytest.mark.parametrize('N,D,A,B', [(3, 10, 5, 33_000), (2, 21, [5, 10], 9_000), (2, 11, 5, 4_100),
-                                     (4, 12, 5, 3_000), (6, 16, 5, 5_000), (9, 22, 5, 2_100), (12, 28, 5, 1_537)])
+                                     (4, 12, 5, 3_000), (6, 16, 5, 5_000), (9, 22, 5, 2_100), (12, 28, 5, 1_537),
+                                     (8, 30, 5, 1_300)])
 def test_tensor_core_and_simt_paths_agree(N, D, A, B):
     """Same weights, same injected noise: logits within 1e-5, sampled indices equal outside the gap band - for
     every team size / head layout the tensor-core kernel covers (resident operands, operand ring + scratch shares,

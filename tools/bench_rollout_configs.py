@@ -10,9 +10,10 @@ import multiagent_rl_b200 as m  # noqa: E402
 from multiagent_rl_b200.networks import random_state_dict  # noqa: E402
 
 CONFIGS = [('simple_spread', None, 65536), ('simple_spread', 6, 65536), ('simple_spread', 9, 32768),
-           ('simple_spread', 12, 32768), ('simple_reference', None, 65536), ('simple_speaker_listener', None, 65536)]
+           ('simple_spread', 12, 32768), ('simple_reference', None, 65536), ('simple_speaker_listener', None, 65536),
+           ('fullobs_collect_treasure', None, 32768)]
 # the same at 1,048,576 envs per GPU (no tail quantisation: thousands of tile pairs per SM)
-CONFIGS += [(s, n, 1 << 20) for s, n, _ in CONFIGS]
+CONFIGS += [(s, n, 1 << 20 if s != 'fullobs_collect_treasure' else 1 << 19) for s, n, _ in CONFIGS]
 IMPL = sys.argv[1] if len(sys.argv) > 1 else 'auto'  # 'tc_fused_large': teams of 6 / 9 / 12 as one kernel per call
 for scen, n, B in CONFIGS:
     env = m.make_env(scen, n=n, num_envs=B, batched=True, seed=1, max_episode_len=25)

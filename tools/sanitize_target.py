@@ -14,7 +14,7 @@ for scen, n, B, A in [('simple_spread', None, 333, 5), ('simple_spread', 6, 70, 
                       ('simple_spread', 12, 37, 5), ('simple_reference', None, 200, [5, 10]),
                       ('simple_speaker_listener', None, 129, 5), ('simple_spread', 1, 33, 5), ('simple_spread', 5, 65, 5),
                       ('simple_spread', 7, 29, 5), ('simple_spread', 8, 31, 5), ('simple_spread', 10, 27, 5),
-                      ('simple_spread', 11, 23, 5)]:
+                      ('simple_spread', 11, 23, 5), ('fullobs_collect_treasure', None, 77, 5)]:
     for precision in ('fp32', 'fp64'):
         env = m.make_env(scen, n=n, num_envs=B, batched=True, seed=3, precision=precision, max_episode_len=3)
         env.track_returns(True)
@@ -27,7 +27,7 @@ for scen, n, B, A in [('simple_spread', None, 333, 5), ('simple_spread', 6, 70, 
         env.observe(); env.get_state(); env.read_stats()
     env = m.make_env(scen, n=n, num_envs=B, batched=True, seed=3, max_episode_len=3)
     obs = env.reset()
-    tc_ok = env.n in (2, 3, 4, 6, 9, 12)
+    tc_ok = env.n in (2, 3, 4, 6, 8, 9, 12)
     for impl in ['simt'] + (['tc'] if tc_ok else []) + (['tc_fused_large'] if env.n in (6, 9, 12) else []):
         actor = m.FusedActor(random_state_dict(env.obs_dim, A, 1), impl=impl)
         actor.forward(obs, want_logits=True, want_onehot=True)
