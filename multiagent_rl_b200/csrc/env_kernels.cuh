@@ -394,7 +394,8 @@ cudaError_t launch_treasure_t(const EnvStateAny &a, const int32_t *act_u, const 
   constexpr int sm = TrLayout<T>::kBlockBytes;
   cudaError_t err = set_smem_once<k_treasure<T, MODE>>(sm);
   if (err != cudaSuccess) return err;
-  const unsigned grid = (unsigned)((a.B + kStepThreads - 1) / kStepThreads);
+  const int64_t per_block = TrLayout<T>::kEnvsPerBlock;  // 8 lanes per env
+  const unsigned grid = (unsigned)((a.B + per_block - 1) / per_block);
   k_treasure<T, MODE><<<grid, kStepThreads, sm, st>>>(typed<T>(a), act_u, mask, auto_len, static_cast<T *>(obs),
                                                       static_cast<T *>(rew), done, info_i);
   return cudaGetLastError();
