@@ -367,7 +367,8 @@ def test_fused_rollout_equals_stepwise_path_tiny_batches(scenario, n, A, impl):
 
 
 @pytest.mark.parametrize('scenario,shards,B', [('simple_spread', 3, 5001), ('simple_spread', 1, 700),
-                                               ('simple_reference', 2, 2050), ('simple_spread', 4, 3)])
+                                               ('simple_reference', 2, 2050), ('simple_spread', 4, 3),
+                                               ('fullobs_collect_treasure', 2, 515)])
 def test_host_rollout_shards_match_the_blocking_calls(scenario, shards, B):
     """HostRollout (non-blocking actor_forward_host_async + mpe_step_host_async per shard and stream) gives, for every
     shard count, exactly the transitions of the device-tensor calls on one env handle: same Philox keys (global env
@@ -376,7 +377,7 @@ def test_host_rollout_shards_match_the_blocking_calls(scenario, shards, B):
     L, seed = 4, 31
     n = None
     A = [5, 10] if scenario == 'simple_reference' else 5
-    D = 21 if scenario == 'simple_reference' else 10
+    D = {'simple_reference': 21, 'fullobs_collect_treasure': 30}.get(scenario, 10)
     actor = m.FusedActor(actor_ref.init_state_dict(D, A, 2), seed=seed)
     hr = m.HostRollout(scenario, B, actor, shards=shards, n=n, seed=seed, max_episode_len=L, track_returns=True)
     env = m.make_env(scenario, n=n, num_envs=B, batched=True, seed=seed, max_episode_len=L)

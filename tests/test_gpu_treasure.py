@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import actor_ref, build_ref, maac_ref, mpe_ref, philox
+from oracle import actor_ref, build_ref, maac_ref, maac_vec, mpe_ref, philox
 
 pytestmark = pytest.mark.gpu
 SC = 'fullobs_collect_treasure'
@@ -91,6 +91,7 @@ def _near_threshold(pos, tr, eps):
     its contact threshold, or do two treasure distances of one agent lie within eps of each other?"""
     B = pos.shape[0]
     near = np.zeros(B, dtype=bool)
+    eps = np.broadcast_to(np.asarray(eps, dtype=np.float64), (B,))[:, None, None]   # scalar or one band per env
     c, d = pos[:, :6], pos[:, 6:]
     dct = np.linalg.norm(c[:, :, None] - tr[:, None], axis=-1)
     near |= (np.abs(dct - 0.075) < eps).any((1, 2))
@@ -218,6 +219,46 @@ def test_rollout_with_the_actor_kernels():
         if (t + 1) % 25 == 0:
             obs = envs[1].reset()
     assert torch.isfinite(rec[0]).all() and rec[1].abs().max() < 200
+
+
+def test_rollout_at_65536_envs_vs_float64_oracle_directly():
+    """BASELINE configs[1] size: a recorded 25-step mpe_rollout (tensor-core actor + step kernel) of 65,536 envs
+    against the vectorised float64 oracle fed the recorded actions, from the kernel's own Philox reset.  Free-running
+    fp32 vs float64 over an episode: positions 5e-4 worst case / 2e-5 at p99.9 (contacts between agents millimetres
+    apart amplify rounding), rewards 2e-3; an env leaves the comparison once a contact flag or a neighbouring pair of
+    the sorted treasure list lies within the band its own position error explains (3 x error + 1e-5)."""
+    import multiagent_rl_b200 as m
+    B, T, seed = 65_536, 25, 20240607
+    env = _make(B, seed=seed, max_episode_len=25)
+    actor = m.FusedActor(actor_ref.init_state_dict(30, 5, 4), seed=seed)
+    obs0 = env.reset()
+    v = maac_vec.VecTreasure(B, seed=seed)
+    assert np.abs(v.reset() - obs0.cpu().numpy()).max() <= 3e-7
+    rec = env.rollout(actor, T, step0=0, record=True)
+    obs, rew, act = (x.cpu().numpy() for x in rec[:3])
+    assert act.min() >= 0 and act.max() <= 4 and len(np.unique(act)) == 5
+    clean = np.ones(B, dtype=bool)    # no contact flag near its threshold so far
+    perr = []
+    for t in range(T):
+        tr_before = v.tr.copy()       # contacts and the sorted list see the treasures as they were BEFORE post_step
+        for l in range(6):            # dead treasures all sit at (-999, -999): move them apart (exact ties go by index)
+            tr_before[tr_before[:, l, 0] < -900, l] = 1000.0 * (l + 2)
+        o, r, _ = v.step(act[t])
+        # an env drops out once a deciding distance (contact thresholds, neighbouring entries of the sorted treasure
+        # list) lies within the band its own fp32 position error explains
+        err = np.abs(obs[t][:, :, 0:2] - v.pos).max((1, 2))
+        clean &= ~_near_threshold(v.pos, tr_before, 3.0 * err + 1e-5)
+        far = np.abs(o) > 100
+        d = np.abs(o - obs[t])
+        perr.append(d[clean][:, :, :4].max(-1).ravel())
+        assert d[clean][~far[clean]].max() <= 5e-4, t
+        assert np.abs(r - rew[t])[clean].max() <= 2e-3, t
+    perr = np.concatenate(perr)
+    assert np.quantile(perr, 0.999) <= 2e-5 and np.median(perr) <= 1e-6
+    assert clean.mean() > 0.9
+    f = env.get_state()[3][:, 0].cpu().numpy().astype(np.int64)
+    # the kernel auto-reset after the 25th step (max_episode_len): compare the state word one step earlier instead
+    assert (v.tstep == 25).all() and clean.sum() > 50_000 and f.shape == (B,)
 
 
 def test_full_size_properties():

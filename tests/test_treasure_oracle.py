@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import build_ref, maac_ref, mpe_ref, philox
+from oracle import build_ref, maac_ref, maac_vec, mpe_ref, philox
 
 P = maac_ref.pack_flags
 
@@ -193,6 +193,28 @@ def test_oracle_reproduces_the_committed_treasure_fixture(golden_dir):
             o, r, d, _ = env.step(_acts(g['act_u'][t, b]))
             assert np.array_equal(np.stack(o), g['obs'][t, b]) and np.array_equal(np.array(r), g['rew'][t, b])
             assert maac_ref.get_flags(env) == g['flags'][t, b]
+
+
+def test_vectorised_oracle_equals_the_loop_oracle(golden_dir):
+    """oracle/maac_vec.py (what the full-size GPU tests compare with) on the fixture: observations, positions, treasure
+    positions, state word and benchmark flags BIT-equal to the loop oracle's committed output; rewards within one ulp
+    (the loop's ``np.linalg.norm`` of the deposit's 1-D mean offset goes through BLAS dot, the vectorised sum does not)."""
+    g = np.load(os.path.join(golden_dir, 'mpe_fullobs_collect_treasure.npz'))
+    T, B = g['act_u'].shape[:2]
+    v = maac_vec.VecTreasure(B, seed=int(g['seed']))
+    v.episode[:] = 0
+    v.set_state(g['pos0'], g['vel0'], g['tr0'], g['flags0'])
+    assert np.array_equal(v.observe(), g['obs0']) and np.array_equal(v.flags(), g['flags0'])
+    for t in range(T):
+        o, r, info = v.step(g['act_u'][t])
+        assert np.array_equal(o, g['obs'][t]) and np.array_equal(v.flags(), g['flags'][t]), t
+        assert np.array_equal(v.pos, g['pos'][t]) and np.array_equal(v.vel, g['vel'][t]) and np.array_equal(v.tr, g['tr'][t])
+        assert np.array_equal(info, g['info'][t]) and np.abs(r - g['rew'][t]).max() <= 6e-17, t
+    # Philox resets: same streams as the kernels (and as PhiloxDraws behind the loop oracle)
+    v2 = maac_vec.VecTreasure(5, seed=11, gid0=5)
+    o = v2.reset()
+    env = _env()
+    assert np.array_equal(np.stack(env.reset()), o[0])
 
 
 @pytest.mark.skipif(not build_ref.available(), reason='oracle/_ref not built (needs /root/reference)')
