@@ -177,6 +177,43 @@ def test_long_run_against_the_loop_oracle(precision, B):
     assert events > 0
 
 
+def test_masked_reset_and_list_surface_with_benchmark_info():
+    """env.reset(mask) restarts only the masked envs (fresh Philox episode, nobody holds, every treasure alive) and
+    leaves the others bit-untouched; the one-env list surface returns upstream's types (list of ndarray(30,), floats,
+    [False] * 8, {'n': [0 / 1 per agent]} with benchmark=True) and turns the caller's action arrays into one-hots."""
+    import multiagent_rl_b200 as m
+    B = 203
+    env = _make(B, seed=8)
+    env.reset()
+    g = torch.Generator().manual_seed(3)
+    for t in range(6):
+        env.step(torch.randint(0, 5, (B, 8), generator=g, dtype=torch.int32))
+    before = [x.clone() for x in env.get_state()]
+    mask = (torch.arange(B) % 3 == 0).to(torch.uint8)
+    obs = env.reset(mask=mask)
+    after = env.get_state()
+    keep = ~mask.bool().cuda()
+    for a, b in zip(after, before):
+        assert torch.equal(a[keep], b[keep])
+    a, t, ty = philox.treasure_reset(8, np.arange(B), 1)
+    sel = mask.bool().numpy()
+    assert np.array_equal(after[0].cpu().numpy()[sel], a[sel]) and not after[1][mask.bool().cuda()].any()
+    want = np.array([maac_ref.pack_flags(ty[b], [True] * 6, [-1] * 6) for b in range(B)])
+    assert np.array_equal(after[3][:, 0].cpu().numpy()[sel], want[sel])
+    assert torch.equal(obs[:, :, 0:2], after[0])
+    # list surface (num_envs = 1, numpy draws) with benchmark info
+    one = m.make_env(SC, benchmark=True)
+    one.seed(5)
+    o = one.reset()
+    assert len(o) == 8 and all(x.shape == (30,) and x.dtype == np.float64 for x in o)
+    acts = [np.array([0.1, 0.7, 0.05, 0.1, 0.05]) for _ in range(8)]
+    o, r, d, info = one.step(acts)
+    assert all(a.tolist() == [0.0, 1.0, 0.0, 0.0, 0.0] for a in acts)          # in place, like upstream
+    assert d == [False] * 8 and len(r) == 8 and all(isinstance(x, float) for x in map(float, r))
+    assert set(info['n']) <= {0, 1} and len(info['n']) == 8
+    assert (np.abs(np.stack(o)[:, 2] - 0.225) < 1e-6).sum() >= 6                 # accelerated to +x: 1.5 * 1.5 * 0.1 (unless in contact)
+
+
 def test_tracked_returns_and_auto_reset():
     """rollout-style use: step + auto-reset after max_episode_len steps, episode statistics folded on the device."""
     B = 300
