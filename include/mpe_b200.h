@@ -18,6 +18,10 @@
  *   - nothing synchronises the host except the *_host entry points, *_destroy
  *     and mpe_stats_read.
  *   - a handle is not thread-safe; handles on different devices are independent.
+ *     One MpeActor may serve several MpeEnv handles on DIFFERENT streams at the same time through mpe_rollout,
+ *     mpe_act_step_host_async (per-env scratch) and actor_forward_host_async (per-slot scratch); plain
+ *     actor_forward calls on one actor must stay on one stream at a time (teams of > 3 agents and two-head actors
+ *     park partial logits in the actor's own scratch buffer).
  *   - "real" is float for MPE_F32 handles and double for MPE_F64 (validation build).
  *   - tensor layouts are row-major with the env index outermost: obs[B][N][D],
  *     rew[B][N], done[B][N], act[B][N].

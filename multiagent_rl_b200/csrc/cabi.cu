@@ -64,6 +64,10 @@ struct MpeEnv {
   // mpe_act_step_host_async: device mirror of the caller's observations and of its transition block
   float *hb_obs_in = nullptr;
   unsigned char *hb_block = nullptr;
+  // dense2-share scratch of the tensor-core actor for launches made on THIS env's stream (mpe_rollout's per-step path,
+  // mpe_act_step_host_async): several env shards share one actor handle on different streams (HostRollout), and the
+  // large-team / two-head actor kernels park partial logits in a scratch buffer - one per stream, not one per actor
+  float *tc_scratch = nullptr;
   bool synced = false;      // all envs are at the same episode step (true after an unmasked reset)
   int32_t host_tstep = 0;   // that common episode step
 };
@@ -73,6 +77,7 @@ constexpr int kHostSlots = 4;  // independent sets of device mirrors: that many 
 struct ActorMirror {
   float *obs = nullptr, *onehot = nullptr;  // device mirrors for actor_forward_host[_async]
   int32_t *act_u = nullptr, *act_c = nullptr;
+  float *tc_scratch = nullptr;  // slots > 0: own dense2-share scratch (slot 0 uses the actor's), see MpeEnv::tc_scratch
   int64_t cap = 0;  // capacity in rows (B*N)
 };
 
@@ -97,6 +102,16 @@ struct MpeReplay {
   int64_t *idx_scratch = nullptr;  // indices drawn by replay_sample when the caller passes none
   int64_t idx_cap = 0;
 };
+
+// The tensor-core actor of large teams (N > 3) and of two-head actors writes per-cell logits shares to a scratch
+// buffer indexed by CTA: two launches in flight on different streams must not share it.
+static bool tc_uses_scratch(const MpeActor *a, int N) { return N > 3 || a->dev.tc.A > 8; }
+static cudaError_t ensure_tc_scratch(float **p, int device) {
+  if (*p != nullptr) return cudaSuccess;
+  int nsm = 0;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+  return cudaMalloc(p, mpe::tc_scratch_floats(nsm > 0 ? nsm : 148) * sizeof(float));
+}
 
 extern "C" {
 
@@ -180,7 +195,7 @@ int mpe_destroy(MpeEnv *env) {
   mpe::EnvStateAny &s = env->st;
   void *ptrs[] = {s.pv, s.lm, s.ep_ret, s.comm, s.goal, s.episode, s.tstep, s.stats,
                   env->h_act_u, env->h_act_c, env->h_obs, env->h_rew, env->h_done, env->r_obs, env->r_act,
-                  env->hb_obs_in, env->hb_block};
+                  env->hb_obs_in, env->hb_block, env->tc_scratch};
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
   delete env;
@@ -381,7 +396,7 @@ int actor_destroy(MpeActor *a) {
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
   for (ActorMirror &m : a->mirror) {
-    void *mp[] = {m.obs, m.onehot, m.act_u, m.act_c};
+    void *mp[] = {m.obs, m.onehot, m.act_u, m.act_c, m.tc_scratch};
     for (void *p : mp)
       if (p != nullptr) cudaFree(p);
   }
@@ -484,7 +499,9 @@ static int actor_forward_host_impl(MpeActor *a, const float *obs_host, int64_t B
     void *old[] = {m.obs, m.onehot, m.act_u, m.act_c};
     for (void *p : old)
       if (p != nullptr) cudaFree(p);
+    float *keep = m.tc_scratch;
     m = ActorMirror();
+    m.tc_scratch = keep;
     CK(cudaMalloc(&m.obs, (size_t)rows * a->dev.D * sizeof(float)));
     CK(cudaMalloc(&m.onehot, (size_t)rows * A * sizeof(float)));
     CK(cudaMalloc(&m.act_u, (size_t)rows * sizeof(int32_t)));
@@ -496,10 +513,16 @@ static int actor_forward_host_impl(MpeActor *a, const float *obs_host, int64_t B
   io.obs = m.obs; io.act_u = m.act_u; io.act_c = a->dev.A1 > 0 ? m.act_c : nullptr;
   io.onehot = onehot_host != nullptr ? m.onehot : nullptr;
   io.B = B; io.N = N; io.seed = seed; io.step = step; io.gid0 = env_id_offset;
-  if (use_tc(a, N, false))
-    CK(mpe::launch_actor_forward_tc(a->dev.tc, io, st));
-  else
+  if (use_tc(a, N, false)) {
+    mpe::TcDev tc = a->dev.tc;
+    if (slot > 0 && tc_uses_scratch(a, N)) {  // slots are in flight on different streams: own scratch each
+      CK(ensure_tc_scratch(&m.tc_scratch, a->device));
+      tc.scratch = m.tc_scratch;
+    }
+    CK(mpe::launch_actor_forward_tc(tc, io, st));
+  } else {
     CK(mpe::launch_actor_forward(a->dev, io, st));
+  }
   if (act_u_host != nullptr) CK(cudaMemcpyAsync(act_u_host, m.act_u, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (act_c_host != nullptr && a->dev.A1 > 0)
     CK(cudaMemcpyAsync(act_c_host, m.act_c, (size_t)rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -568,10 +591,16 @@ int mpe_act_step_host_async(MpeEnv *env, MpeActor *actor, const float *obs_host,
   io.act_u = reinterpret_cast<int32_t *>(blk + l.off_act_u);
   io.act_c = actor->dev.A1 > 0 ? reinterpret_cast<int32_t *>(blk + l.off_act_c) : nullptr;
   io.B = s.B; io.N = s.N; io.seed = s.seed; io.step = step; io.gid0 = s.gid0;
-  if (use_tc(actor, s.N, false))
-    CK(mpe::launch_actor_forward_tc(actor->dev.tc, io, st));
-  else
+  if (use_tc(actor, s.N, false)) {
+    mpe::TcDev tc = actor->dev.tc;
+    if (tc_uses_scratch(actor, s.N)) {  // shards share the actor handle on different streams: scratch per env handle
+      CK(ensure_tc_scratch(&env->tc_scratch, env->device));
+      tc.scratch = env->tc_scratch;
+    }
+    CK(mpe::launch_actor_forward_tc(tc, io, st));
+  } else {
     CK(mpe::launch_actor_forward(actor->dev, io, st));
+  }
   CK(mpe::launch_step(s, io.act_u, io.act_c, nullptr, blk + l.off_obs, blk + l.off_rew, blk + l.off_done, nullptr, nullptr, st));
   if (s.track) env->host_tstep += 1; else env->synced = false;
   CK(cudaMemcpyAsync(block_host, blk, l.bytes, cudaMemcpyDeviceToHost, st));
@@ -624,7 +653,12 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
       CK(mpe::launch_observe(env->st, env->r_obs, st));
       io.obs_work = env->r_obs;
     }
-    CK(mpe::launch_rollout_tc(env->st, actor->dev.tc, io, st));
+    mpe::TcDev tcw = actor->dev.tc;
+    if (tc_uses_scratch(actor, env->st.N)) {
+      CK(ensure_tc_scratch(&env->tc_scratch, env->device));
+      tcw.scratch = env->tc_scratch;
+    }
+    CK(mpe::launch_rollout_tc(env->st, tcw, io, st));
     env->synced = false;
     return MPE_OK;
   }
@@ -647,6 +681,11 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
       CK(cudaMalloc(&env->r_act, (size_t)rows * 2 * sizeof(int32_t)));
     }
     const bool tc = use_tc(actor, s.N, false);
+    mpe::TcDev tcw = actor->dev.tc;
+    if (tc && tc_uses_scratch(actor, s.N)) {  // rollouts of several envs may share one actor on different streams
+      CK(ensure_tc_scratch(&env->tc_scratch, env->device));
+      tcw.scratch = env->tc_scratch;
+    }
     CK(mpe::launch_observe(s, env->r_obs, st));
     const float *cur = env->r_obs;
     const int L = s.max_episode_len;
@@ -656,7 +695,7 @@ int mpe_rollout(MpeEnv *env, MpeActor *actor, int32_t T, uint64_t step0, float *
       aio.act_u = act_u != nullptr ? act_u + (int64_t)t * rows : env->r_act;
       if (s.act_c > 0) aio.act_c = act_c != nullptr ? act_c + (int64_t)t * rows : env->r_act + rows;
       if (tc)
-        CK(mpe::launch_actor_forward_tc(actor->dev.tc, aio, st));
+        CK(mpe::launch_actor_forward_tc(tcw, aio, st));
       else
         CK(mpe::launch_actor_forward(actor->dev, aio, st));
       float *o = obs_next != nullptr ? obs_next + (int64_t)t * rows * s.D : env->r_obs;

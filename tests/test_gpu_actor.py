@@ -368,7 +368,8 @@ def test_fused_rollout_equals_stepwise_path_tiny_batches(scenario, n, A, impl):
 
 @pytest.mark.parametrize('scenario,shards,B', [('simple_spread', 3, 5001), ('simple_spread', 1, 700),
                                                ('simple_reference', 2, 2050), ('simple_spread', 4, 3),
-                                               ('fullobs_collect_treasure', 2, 515)])
+                                               ('fullobs_collect_treasure', 2, 515),
+                                               ('fullobs_collect_treasure', 4, 20_011)])
 def test_host_rollout_shards_match_the_blocking_calls(scenario, shards, B):
     """HostRollout (non-blocking actor_forward_host_async + mpe_step_host_async per shard and stream) gives, for every
     shard count, exactly the transitions of the device-tensor calls on one env handle: same Philox keys (global env

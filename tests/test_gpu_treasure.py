@@ -214,6 +214,26 @@ def test_masked_reset_and_list_surface_with_benchmark_info():
     assert (np.abs(np.stack(o)[:, 2] - 0.225) < 1e-6).sum() >= 6                 # accelerated to +x: 1.5 * 1.5 * 0.1 (unless in contact)
 
 
+def test_sharding_is_invariant_to_the_number_of_shards():
+    """envs shard in contiguous blocks, reset and respawn streams are keyed by the GLOBAL env id - one env
+    of 96 instances and three shards of 32 with env_id_offset give bit-identical trajectories (30 steps: respawns occur)."""
+    whole = _make(96, seed=21)
+    parts = [_make(32, seed=21, env_id_offset=32 * k) for k in range(3)]
+    o = whole.reset()
+    assert torch.equal(o, torch.cat([p.reset() for p in parts]))
+    g = torch.Generator().manual_seed(9)
+    changed = 0
+    for t in range(30):
+        act = torch.randint(0, 5, (96, 8), generator=g, dtype=torch.int32)
+        f0 = _flags(whole)
+        o, r, _, _ = whole.step(act)
+        outs = [p.step(act[32 * k:32 * k + 32]) for k, p in enumerate(parts)]
+        assert torch.equal(o, torch.cat([x[0] for x in outs])) and torch.equal(r, torch.cat([x[1] for x in outs])), t
+        assert np.array_equal(_flags(whole), np.concatenate([_flags(p) for p in parts]))
+        changed += int((_flags(whole) != f0).sum())
+    assert changed > 0
+
+
 def test_tracked_returns_and_auto_reset():
     """rollout-style use: step + auto-reset after max_episode_len steps, episode statistics folded on the device."""
     B = 300
