@@ -303,6 +303,8 @@ def run_b200(args):
     sync_all()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
+    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin (outside every event pair): the host enqueues ahead of the GPU, so no
+    #                                event pair contains a wait for a launch that Python had not issued yet
     for k in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the event pair)
         ev[k][0].record()
@@ -489,6 +491,7 @@ def side_measurements(m, actor, dev, pk, off):
     torch.cuda.synchronize()
     reps = 48
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
     e0.record()
     for i in range(reps):
         env.step(act, out=rot[i % 4])  # 280 MB of algorithmic traffic per launch, outputs rotate over 566 MB
@@ -512,6 +515,7 @@ def side_measurements(m, actor, dev, pk, off):
     for _ in range(2):
         actor.forward(obs[:262144])
     torch.cuda.synchronize()
+    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
     e0.record()
     for _ in range(5):
         actor.forward(obs[:262144])
@@ -534,6 +538,7 @@ def side_measurements(m, actor, dev, pk, off):
     for t in range(3):
         fused(t)
     torch.cuda.synchronize()
+    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
     e0.record()
     for t in range(20):
         fused(3 + t)
@@ -564,6 +569,7 @@ def side_measurements(m, actor, dev, pk, off):
         fused_shard(i % nsh, i // nsh)
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10 * nsh)]
+    torch.cuda._sleep(20_000_000)
     for i, (a, b) in enumerate(evs):
         a.record()
         fused_shard(i % nsh, 2 + i // nsh)

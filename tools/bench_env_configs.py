@@ -34,6 +34,7 @@ def run(dev, peak, verbose=False, reps=30):
             env.step(au, ac, out=bufs)
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
         e0.record()
         for _ in range(reps):
             env.step(au, ac, out=bufs)  # working set per launch is > 126 MB L2 for every config

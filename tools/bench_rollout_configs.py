@@ -24,6 +24,7 @@ for scen, n, B in CONFIGS:
     env.rollout(actor, T)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
     e0.record()
     for _ in range(4):
         env.rollout(actor, T)
