@@ -110,7 +110,8 @@ int mpe_observe(MpeEnv *env, void *obs_out, void *stream);
  * MPE_COLLECT_TREASURE (experiments/scenarios.py:95-121,174-190 + the MAAC fork's scenario): sensitivity = accel,
  *   mass-aware contact forces, max_speed clip; observation / reward are taken BEFORE Scenario.post_step (pick-up,
  *   respawn, deposit), which runs at the end of the same kernel; info_i [B][N+1] = benchmark_data per agent (0 / 1)
- *   and a zero; info_f is not written. */
+ *   and a zero; info_f is not written.  The per-env episode step counter advances whether or not returns are tracked
+ *   (it keys the respawn draws). */
 int mpe_step(MpeEnv *env, const int32_t *act_u, const int32_t *act_c, const void *comm_vec, void *obs,
              void *rew, uint8_t *done, int32_t *info_i, void *info_f, void *stream);
 
