@@ -62,7 +62,7 @@ __device__ __forceinline__ T tr_shfl(T v, int src) {
 
 // MODE 0: env.step   1: env.reset (masked / timed-out envs) + observation   2: observation only
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kStepThreads, std::is_same<T, float>::value ? 8 : 1)  // fp32: 64 registers, 32 warps per SM
+__global__ void __launch_bounds__(kStepThreads, std::is_same<T, float>::value ? 10 : 1)  // fp32: 48 registers, 40 warps per SM (8: 62 registers, 77.0 us; 10: 76.2; 12: spills, 77.9)
     k_treasure(EnvState<T> s, const int32_t *__restrict__ act_u, const uint8_t *__restrict__ mask, int auto_len,
                T *__restrict__ obs, T *__restrict__ rew, uint8_t *__restrict__ done, int32_t *__restrict__ info_i) {
   extern __shared__ __align__(128) unsigned char smem[];
