@@ -796,13 +796,8 @@ int replay_create(const ReplayConfig *cfg, MpeReplay **out) {
   r->device = cfg->device;
   mpe::ReplayDev &d = r->dev;
   d.capacity = cfg->capacity; d.N = cfg->num_agents; d.D = cfg->obs_dim; d.A0 = cfg->act0; d.A1 = cfg->act1;
-  const size_t C = (size_t)d.capacity, R = (size_t)d.N * d.D;
-  cudaError_t e = cudaMalloc(&d.obs, C * R * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&d.obs_next, C * R * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&d.act_u, C * d.N);
-  if (e == cudaSuccess) e = cudaMalloc(&d.act_c, C * d.N);
-  if (e == cudaSuccess) e = cudaMalloc(&d.rew, C * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&d.done, C * sizeof(float));
+  d.rec_bytes = mpe::ReplayDev::record_bytes(d.N, d.D);
+  cudaError_t e = cudaMalloc(&d.ring, (size_t)d.capacity * (size_t)d.rec_bytes);
   if (e != cudaSuccess) {
     replay_destroy(r);
     return fail_cuda(e, "replay_create: cudaMalloc");
@@ -815,7 +810,7 @@ int replay_destroy(MpeReplay *r) {
   if (r == nullptr) return MPE_OK;
   DeviceGuard g(r->device);
   cudaDeviceSynchronize();
-  void *ptrs[] = {r->dev.obs, r->dev.obs_next, r->dev.act_u, r->dev.act_c, r->dev.rew, r->dev.done, r->idx_scratch};
+  void *ptrs[] = {r->dev.ring, r->idx_scratch};
   for (void *p : ptrs)
     if (p != nullptr) cudaFree(p);
   delete r;

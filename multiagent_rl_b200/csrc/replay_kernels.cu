@@ -1,47 +1,63 @@
 // Device-resident replay ring (SURVEY section 8f "next" row 1): rls/replay_buffer.py:9-91 (ReplayBuffer.add /
 // make_index / sample_index / _encode_sample) and the transition tuple built at experiments/run.py:46,52
 // (obs_n, action_n_env, rew_shared = sum(rew_n), new_obs_n, float(done)), for B env instances at a time.
-// Transitions stay in HBM in the caller-facing layouts; both kernels are pure streaming copies/gathers
-// (16 B vector accesses, one warp per transition row).
+// A transition is one contiguous record of the ring (replay_launch.h); add is a streaming copy into consecutive
+// records, sample a gather of whole records.
 #include "replay_launch.h"
 
 #include "common.cuh"
 
 namespace mpe {
 
-// Both kernels are element-parallel over the flattened [rows][R] observation arrays (8 B vectors when R is even), so
-// every lane moves data even though one transition is only R * 4 = 120 B (simple_spread N = 3); the per-row
-// extras (action indices, shared reward, done flag) are handled by the first threads of each row.
-
-// append B transitions at ring slots (head + b) % capacity
-template <int V>  // V = floats per vector (2 or 1)
-__global__ void __launch_bounds__(256) k_replay_add(ReplayDev r, int64_t head, int64_t B, const float *__restrict__ obs,
+// add: ring slots (head + b) % capacity are contiguous apart from one wrap, so the host splits the batch at the wrap and
+// a segment fills CONSECUTIVE records.  A block assembles `rpb` records in shared memory (256 / rpb threads per row:
+// coalesced reads of the caller's obs / obs_next rows, the action bytes, the shared reward) and writes them out as one
+// contiguous, 16 B-vectorised span - writing the record fields straight from the source layout (8 B stores into
+// alternating 120 B halves of 256 B records) reached 0.54 of HBM, separate arrays 0.95 for the add but 0.47 for sample.
+template <int V>  // floats per vector of the observation copies: 2 (R even, 8 B aligned sources) or 1
+__global__ void __launch_bounds__(256) k_replay_add(ReplayDev r, int64_t slot0, int64_t rows, int rpb, const float *__restrict__ obs,
                                                     const int32_t *__restrict__ act_u, const int32_t *__restrict__ act_c,
                                                     const float *__restrict__ rew, const float *__restrict__ obs_next,
                                                     const float *__restrict__ done) {
-  const int R = r.N * r.D, RV = R / V;
-  const int64_t total = B * RV;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / RV;
-    const int c = (int)(i - b * RV);
-    const int64_t slot = (head + b) % r.capacity;
-    if (V == 2) {
-      reinterpret_cast<float2 *>(r.obs + slot * R)[c] = reinterpret_cast<const float2 *>(obs + b * R)[c];
-      reinterpret_cast<float2 *>(r.obs_next + slot * R)[c] = reinterpret_cast<const float2 *>(obs_next + b * R)[c];
-    } else {
-      r.obs[slot * R + c] = obs[b * R + c];
-      r.obs_next[slot * R + c] = obs_next[b * R + c];
+  extern __shared__ __align__(16) unsigned char tile[];
+  const int R = r.N * r.D, RV = R / V, rec = (int)r.rec_bytes;
+  const int dj = 256 / RV, dc = 256 - dj * RV;  // (row, column) of a flat vector index advance by this per 256 threads
+  for (int64_t b0 = (int64_t)blockIdx.x * rpb; b0 < rows; b0 += (int64_t)gridDim.x * rpb) {
+    const int nrows = (int)((rows - b0) < rpb ? (rows - b0) : rpb);
+    // phase 1: the block's rows of obs / obs_next are one contiguous span each: flat, coalesced reads; the shared-memory
+    // address of an element follows from its (row, column), advanced incrementally
+    {
+      int row = threadIdx.x / RV, c = threadIdx.x - row * RV;
+      const float *so = obs + b0 * R, *sn = obs_next + b0 * R;
+      for (int e = threadIdx.x; e < nrows * RV; e += 256, row += dj, c += dc) {
+        if (c >= RV) { c -= RV; ++row; }
+        unsigned char *rp = tile + row * rec;
+        if (V == 2) {
+          reinterpret_cast<float2 *>(rp)[c] = reinterpret_cast<const float2 *>(so)[e];
+          reinterpret_cast<float2 *>(rp + r.off_next())[c] = reinterpret_cast<const float2 *>(sn)[e];
+        } else {
+          reinterpret_cast<float *>(rp)[c] = so[e];
+          reinterpret_cast<float *>(rp + r.off_next())[c] = sn[e];
+        }
+      }
     }
-    if (c < r.N) {
-      r.act_u[slot * r.N + c] = (int8_t)act_u[b * r.N + c];
-      r.act_c[slot * r.N + c] = act_c != nullptr ? (int8_t)act_c[b * r.N + c] : (int8_t)0;
+    for (int e = threadIdx.x; e < nrows * r.N; e += 256) {
+      const int row = e / r.N, n = e - row * r.N;
+      tile[row * rec + r.off_au() + n] = (unsigned char)(int8_t)act_u[b0 * r.N + e];
+      tile[row * rec + r.off_ac() + n] = act_c != nullptr ? (unsigned char)(int8_t)act_c[b0 * r.N + e] : (unsigned char)0;
     }
-    if (c == 0) {
+    for (int row = threadIdx.x; row < nrows; row += 256) {
       float s = 0.0f;  // rew_shared = np.sum(rew_n) (experiments/run.py:46), agent order
-      for (int n = 0; n < r.N; ++n) s += rew[b * r.N + n];
-      r.rew[slot] = s;
-      r.done[slot] = done != nullptr ? done[b] : 0.0f;
+      for (int n = 0; n < r.N; ++n) s += rew[(b0 + row) * r.N + n];
+      *reinterpret_cast<float *>(tile + row * rec + r.off_rew()) = s;
+      *reinterpret_cast<float *>(tile + row * rec + r.off_done()) = done != nullptr ? done[b0 + row] : 0.0f;
     }
+    __syncthreads();
+    // phase 2: nrows consecutive records = one contiguous span of the ring, 16 B per lane
+    uint4 *dst = reinterpret_cast<uint4 *>(r.ring + (slot0 + b0) * r.rec_bytes);
+    const uint4 *src = reinterpret_cast<const uint4 *>(tile);
+    for (int v = threadIdx.x; v < nrows * (rec / 16); v += 256) dst[v] = src[v];
+    __syncthreads();
   }
 }
 
@@ -54,7 +70,10 @@ __global__ void __launch_bounds__(256) k_replay_make_index(int64_t size, int64_t
   }
 }
 
-// gather `batch` transitions by index
+// gather `batch` transitions by index, element-parallel over the flattened [batch][R] output (8 B vectors when R is
+// even): every lane moves data although one transition is only R * 4 = 120 B (simple_spread N = 3), and a warp's stores
+// are one aligned 256 B span.  (Measured and not kept: 16 lanes per row with shift / mask indexing instead of the two
+// divisions per element - 0.37 of HBM, with 4 rows in flight per lane group 0.30, against 0.47 for this form.)
 template <int V>
 __global__ void __launch_bounds__(256) k_replay_gather(ReplayDev r, int64_t size, int64_t batch, const int64_t *__restrict__ idx,
                                                        float *__restrict__ obs, float *__restrict__ act_onehot,
@@ -62,31 +81,37 @@ __global__ void __launch_bounds__(256) k_replay_gather(ReplayDev r, int64_t size
                                                        float *__restrict__ done) {
   const int R = r.N * r.D, RV = R / V, A = r.A0 + r.A1;
   const int64_t total = batch * RV;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t j = i / RV;
-    const int c = (int)(i - j * RV);
+  // (row, column) of flat element i advance incrementally with the grid stride: two divisions per THREAD, none per element
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t dj = stride / RV;
+  const int dc = (int)(stride - dj * RV);
+  int64_t j = i0 / RV;
+  int c = (int)(i0 - j * RV);
+  for (int64_t i = i0; i < total; i += stride, j += dj, c += dc) {
+    if (c >= RV) { c -= RV; ++j; }
     // list indexing of ReplayBuffer._storage[i] (rls/replay_buffer.py:42): negative indices count from the end;
     // anything still outside [0, size) is clamped so that a stale index can never read outside the ring
     int64_t slot = idx[j];
     if (slot < 0) slot += size;
     slot = slot < 0 ? 0 : (slot >= size ? size - 1 : slot);
+    const unsigned char *rec = r.ring + slot * r.rec_bytes;  // the whole transition: one contiguous record
     if (V == 2) {
-      if (obs != nullptr) reinterpret_cast<float2 *>(obs + j * R)[c] = reinterpret_cast<const float2 *>(r.obs + slot * R)[c];
+      if (obs != nullptr) reinterpret_cast<float2 *>(obs + j * R)[c] = reinterpret_cast<const float2 *>(rec)[c];
       if (obs_next != nullptr)
-        reinterpret_cast<float2 *>(obs_next + j * R)[c] = reinterpret_cast<const float2 *>(r.obs_next + slot * R)[c];
+        reinterpret_cast<float2 *>(obs_next + j * R)[c] = reinterpret_cast<const float2 *>(rec + r.off_next())[c];
     } else {
-      if (obs != nullptr) obs[j * R + c] = r.obs[slot * R + c];
-      if (obs_next != nullptr) obs_next[j * R + c] = r.obs_next[slot * R + c];
+      if (obs != nullptr) obs[j * R + c] = reinterpret_cast<const float *>(rec)[c];
+      if (obs_next != nullptr) obs_next[j * R + c] = reinterpret_cast<const float *>(rec + r.off_next())[c];
     }
     if (act_onehot != nullptr)
       for (int e = c; e < r.N * A; e += RV) {
         const int n = e / A, a = e - n * A;
-        const int u = r.act_u[slot * r.N + n], cc = r.act_c[slot * r.N + n];
+        const int u = reinterpret_cast<const int8_t *>(rec + r.off_au())[n], cc = reinterpret_cast<const int8_t *>(rec + r.off_ac())[n];
         act_onehot[j * r.N * A + e] = (a < r.A0 ? a == u : a - r.A0 == cc) ? 1.0f : 0.0f;
       }
     if (c == 0) {
-      if (rew != nullptr) rew[j] = r.rew[slot];
-      if (done != nullptr) done[j] = r.done[slot];
+      if (rew != nullptr) rew[j] = *reinterpret_cast<const float *>(rec + r.off_rew());
+      if (done != nullptr) done[j] = *reinterpret_cast<const float *>(rec + r.off_done());
     }
   }
 }
@@ -100,12 +125,28 @@ cudaError_t launch_replay_add(const ReplayDev &r, int64_t head, int64_t B, const
                               const int32_t *act_c, const float *rew, const float *obs_next, const float *done,
                               cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  const int R = r.N * r.D;
-  const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(obs_next)) & 7) == 0;
-  if (v2)
-    k_replay_add<2><<<grid_for(B * (R / 2)), 256, 0, st>>>(r, head, B, obs, act_u, act_c, rew, obs_next, done);
-  else
-    k_replay_add<1><<<grid_for(B * R), 256, 0, st>>>(r, head, B, obs, act_u, act_c, rew, obs_next, done);
+  const int64_t R = (int64_t)r.N * r.D;
+  int rpb = 128;  // records per block: as many as fit into 32 KB of shared memory
+  while (rpb > 1 && (int64_t)rpb * r.rec_bytes > 32 * 1024) rpb >>= 1;
+  if (r.rec_bytes > 48 * 1024) return cudaErrorInvalidValue;
+  int64_t row0 = 0;
+  while (row0 < B) {  // at most capacity rows per segment; a batch larger than the ring wraps more than once
+    const int64_t slot0 = (head + row0) % r.capacity;
+    const int64_t rows = (B - row0) < (r.capacity - slot0) ? (B - row0) : (r.capacity - slot0);
+    const int64_t blocks = (rows + rpb - 1) / rpb;
+    const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);
+    const size_t sm = (size_t)rpb * r.rec_bytes;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(obs + row0 * R) | reinterpret_cast<uintptr_t>(obs_next + row0 * R);
+    if (R % 2 == 0 && (al & 7) == 0)
+      k_replay_add<2><<<grid, 256, sm, st>>>(r, slot0, rows, rpb, obs + row0 * R, act_u + row0 * r.N,
+                                             act_c != nullptr ? act_c + row0 * r.N : nullptr, rew + row0 * r.N,
+                                             obs_next + row0 * R, done != nullptr ? done + row0 : nullptr);
+    else
+      k_replay_add<1><<<grid, 256, sm, st>>>(r, slot0, rows, rpb, obs + row0 * R, act_u + row0 * r.N,
+                                             act_c != nullptr ? act_c + row0 * r.N : nullptr, rew + row0 * r.N,
+                                             obs_next + row0 * R, done != nullptr ? done + row0 : nullptr);
+    row0 += rows;
+  }
   return cudaGetLastError();
 }
 

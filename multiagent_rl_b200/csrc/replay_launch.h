@@ -5,12 +5,19 @@
 
 namespace mpe {
 
+// One transition = one contiguous record of the ring, so that a uniformly sampled transition is ONE DRAM burst:
+//   [obs N*D f32][obs_next N*D f32][shared reward f32][done f32][act_u N int8][act_c N int8] padded to 16 B
+// (256 B for simple_spread N = 3).  With six separate arrays a sample touched 2 x (4-5) + 4 sectors for 250 B of payload.
 struct ReplayDev {
-  float *obs = nullptr, *obs_next = nullptr;  // [capacity][N][D]
-  int8_t *act_u = nullptr, *act_c = nullptr;  // [capacity][N] head indices
-  float *rew = nullptr, *done = nullptr;      // [capacity] shared reward, done flag
-  int64_t capacity = 0;
+  unsigned char *ring = nullptr;  // [capacity][rec_bytes]
+  int64_t capacity = 0, rec_bytes = 0;
   int32_t N = 0, D = 0, A0 = 0, A1 = 0;
+  __host__ __device__ int64_t off_next() const { return (int64_t)N * D * 4; }
+  __host__ __device__ int64_t off_rew() const { return (int64_t)N * D * 8; }
+  __host__ __device__ int64_t off_done() const { return off_rew() + 4; }
+  __host__ __device__ int64_t off_au() const { return off_rew() + 8; }
+  __host__ __device__ int64_t off_ac() const { return off_au() + N; }
+  __host__ __device__ static int64_t record_bytes(int N, int D) { return ((int64_t)N * D * 8 + 8 + 2 * N + 15) / 16 * 16; }
 };
 
 cudaError_t launch_replay_add(const ReplayDev &r, int64_t head, int64_t B, const float *obs, const int32_t *act_u,
