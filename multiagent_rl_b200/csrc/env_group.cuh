@@ -48,7 +48,9 @@ struct GroupLayout {
   static constexpr int kPad = kF32 ? 0 : ((R * (int)sizeof(T)) % 16 == 0 ? 16 / (int)sizeof(T) : 0);
   static constexpr bool kPerEnv = kPad != 0;
   static constexpr int RS = R + kPad;
-  static constexpr int kWarpBytes = ((EPW * RS + EPW * N) * (int)sizeof(T) + 127) / 128 * 128;
+  // rewards are NOT staged (3 plain stores per lane): the tile is the occupancy limit of these kernels (N = 9: 8,320 ->
+  // 7,936 B per warp = 7 instead of 6 resident CTAs per SM)
+  static constexpr int kWarpBytes = (EPW * RS * (int)sizeof(T) + 127) / 128 * 128;
   static constexpr int kBlockBytes = kWarpBytes * (kGroupStepThreads / 32);
   static_assert(N % G == 0, "agents must split evenly over the lanes of an env");
 };
@@ -80,8 +82,7 @@ __device__ __forceinline__ bool grp_emit(const GroupLanes<T, N, G> &g, const T (
   // smem == nullptr: no staging buffer (the fused rollout's env phase) - rows go straight to global memory
   const bool obs_tma = smem != nullptr && full && obs != nullptr && (reinterpret_cast<uintptr_t>(obs + b0 * R) & 15) == 0 &&
                        (GL::kPerEnv || (EPW * R * sizeof(T)) % 16 == 0);
-  const bool rew_tma = smem != nullptr && full && rew != nullptr && (reinterpret_cast<uintptr_t>(rew + b0 * N) & 15) == 0 &&
-                       ((EPW * N * sizeof(T)) % 16 == 0);
+  const bool rew_tma = false;  // see GroupLayout::kWarpBytes
   if (obs != nullptr && obs_tma && GL::kVec > 1) {
     // shared-memory staging with vector stores (the pointer is derived from the shared array only, so these are STS)
     float *rowbase = reinterpret_cast<float *>(smem + warp * GL::kWarpBytes) + el * RS + q * A * D;
