@@ -2,14 +2,16 @@
 // agents and A landmarks in registers; positions travel between the lanes of an env by warp shuffle.
 //
 // Why: the thread-per-env kernel needs every entity of the env in one thread's registers (255 registers and
-// spills at N >= 9, 8 warps/SM) and walks N(N-1)/2 pairs serially.  Here a lane evaluates only the forces on
-// its OWN agents (each pair is evaluated by both owners - twice the flops, no atomics, G x the parallelism)
-// and needs ~80 registers.  Results are bit-identical to the thread-per-env kernel:
-//   * the force on agent i from the pair {i, j} is 100 (p_i - p_j) / dist * pen for either ordering, because
-//     upstream's f_b = -f with delta = p_a - p_b negates exactly;
-//   * contributions are added in the order of the other agent's index, which is upstream's (a, b)
-//     lexicographic pair order seen from agent i;
-//   * the landmark terms of the reward are summed in landmark order by every lane.
+// spills at N >= 9, 8 warps/SM) and walks N(N-1)/2 pairs serially.  Here a lane keeps only its OWN agents (no atomics,
+// G x the parallelism, 56-64 registers).
+//   fp64 (validation build): every pair is evaluated by both owners and a lane adds the contributions in the order of
+//     the other agent's index, which is upstream's (a, b) lexicographic pair order seen from agent i - the force on
+//     agent i from the pair {i, j} is 100 (p_i - p_j) / dist * pen for either ordering, because upstream's f_b = -f
+//     with delta = p_a - p_b negates exactly: same bits as the thread-per-env kernel;
+//   fp32: most pairs ONCE (grp_physics: own-block pairs once, one partner block per block distance with the negated
+//     forces handed over by shuffle): half the contact evaluations at N = 9, a different accumulation order (fp32
+//     tolerance against the oracle; k_step_grp and the fused large-team rollout share the code and stay bit-identical);
+//   the landmark terms of the reward are summed in landmark order by every lane.
 // Reference rows: World.apply_environment_force / get_collision_force / integrate_state, simple_spread
 // Scenario.reward / benchmark_data (multiagent package, called from experiments/run.py:44) and
 // experiments/scenarios.py:6-20 (observation); make_world(num_agents=n) at experiments/scenarios.py:170.
