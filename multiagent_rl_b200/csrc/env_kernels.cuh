@@ -17,6 +17,9 @@ constexpr int kStepThreads = 128;
 namespace mpe {
 
 constexpr int kStageMaxBytes = 16384;  // per-warp obs staging above this falls back to per-agent staging
+// rewards leave through a coalesced copy of the staged values instead of a second bulk store per warp (measured:
+// simple_reference 0.857 -> 0.877 of HBM, the others unchanged)
+constexpr bool kStageRewards = false;
 
 template <typename T, int SC, int N>
 struct StageLayout {
@@ -40,7 +43,7 @@ __device__ __forceinline__ void emit_outputs(const Env<T, SC, N> &e, const T (*c
   T *st_rew = st_obs + SL::kObsElems;
   // TMA bulk stores need 16 B aligned global addresses (warp spans are multiples of 128 B)
   const bool obs_tma = SL::kFull && (reinterpret_cast<uintptr_t>(obs) & 15) == 0;
-  const bool rew_tma = (reinterpret_cast<uintptr_t>(rew) & 15) == 0;
+  const bool rew_tma = kStageRewards && (reinterpret_cast<uintptr_t>(rew) & 15) == 0;
   if (full) {
     bool issued = false;
     if (obs != nullptr) {
