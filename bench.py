@@ -584,6 +584,8 @@ def side_measurements(m, actor, dev, pk, off):
     sys.path.insert(0, os.path.join(ROOT, 'tools'))
     import bench_env_configs
     out['env_step_configs'] = bench_env_configs.run(dev, pk['hbm_gbs'])  # configs 3/4: env-only HBM fractions
+    import bench_replay
+    out['replay'] = bench_replay.run(dev, pk['hbm_gbs'])  # device replay ring, add / uniform sample
     return out
 
 
