@@ -8,35 +8,40 @@
 // are the MAAC fork's multiagent/core.py and scenarios/fullobs_collect_treasure.py as restated in
 // oracle/maac_ref.py (parity unpinned: the fork is not in the reference tree; the four ambiguities are listed there).
 //
-// Mapping: ONE LANE PER AGENT, 8 lanes per env, 4 envs per warp.  Lane q of an env owns agent q (position, velocity)
-// and, for q < 6, treasure q; everything another lane needs travels by warp shuffle:
-//   * forces: a lane evaluates the 7 contacts of its own agent, adding them in the order of the other agent's index -
-//     upstream's (a, b) lexicographic pair order seen from that agent; the mass ratio is applied from the lane's own
-//     side (f_a = r f and f_b = -(1/r) f negate exactly, so either side computes the bits upstream computes);
-//   * observation: 6 treasure positions by shuffle, 15 comparisons give every treasure its rank in the sorted list and
-//     its entry is stored at the rank's offset of the lane's row in shared memory; the warp's 32 rows are one
-//     contiguous 3,840 B span of obs[b][8][30] and leave with ONE cp.async.bulk issued by lane 0;
-//   * rewards: every lane from its own distances (collector: contacts with collectors, nearest treasure or its deposit;
-//     deposit: nearest matching holder or the mean offset of the others); the global term is a 3-step xor reduction;
-//   * post_step (pick-up / respawn / deposit): the 6 x 8 contact bits are gathered by 6 shuffles and every lane runs the
-//     same integer logic on the env's state word; lane l keeps treasure l.
+// Mapping: 4 LANES PER ENV, 8 envs per warp.  Lane q of an env owns agents 2q and 2q + 1 (lanes 0..2: the six
+// collectors, lane 3: the two deposits - a lane's two agents share mass, size and role) and, for q < 3, treasures 2q
+// and 2q + 1; everything another lane needs travels by warp shuffle:
+//   * forces, fp32: most pairs ONCE - the pair inside the lane's block once (applied to both agents), the 2 x 2 pairs
+//     against block q + 1 evaluated here and handed (negated) to that block's lane through the same shuffles that bring
+//     block q - 1's, the opposite block q + 2 from both sides: 9 contact evaluations per lane for 28 pairs per env.
+//     fp64: every agent adds its 7 contacts in the order of the other agent's index (upstream's (a, b) lexicographic
+//     pair order seen from that agent); the mass ratio is applied from the lane's own side (f_a = r f and
+//     f_b = -(1/r) f negate exactly, so either side computes the bits upstream computes);
+//   * observation: 6 treasure positions by shuffle; 15 comparisons give every treasure its rank in an agent's sorted
+//     list and its entry is stored at the rank's offset of the agent's row in shared memory; the warp's 64 rows are
+//     one contiguous 7,680 B span of obs[b][8][30] and leave with ONE cp.async.bulk issued by lane 0;
+//   * rewards: every lane from its own agents' distances; the global term is one REDUX over the env's 4 lanes;
+//   * post_step (pick-up / respawn / deposit): replicated integer logic on the env's state word behind warp-uniform
+//     early-outs (a pick-up or a deposit happens in a few per cent of the env steps).
 // Per-env integer state is one word (EnvState::goal):
 //   bit l        type of treasure l (two types = the two deposits)
 //   bit 6 + l    treasure l is alive (a collected treasure sits at (-999, -999) until it respawns one step later)
 //   bits 12+2i   what collector i holds: 0 = nothing, 1 + type otherwise
-// History (ncu digests in profiles/r2_ncu_treasure.txt): the thread-per-env versions (every entity in one thread's
-// registers, 168 registers, 12 warps per SM) were latency bound at 0.42 -> 0.64 of HBM.
+// History (ncu digests in profiles/r2_ncu_treasure.txt): thread per env (168 registers, 12 warps per SM, latency
+// bound) 0.42 -> 0.64 of HBM; one lane per agent (instruction bound: 929 warp instructions per 4 envs, the per-lane
+// setup / decoding / reductions replicated 8 times per env) 0.70.
 #pragma once
 #include "env_core.cuh"
 
 namespace mpe {
 
 constexpr int kTrN = 8, kTrC = 6, kTrL = 6, kTrD = 30, kTrR = kTrN * kTrD;
-constexpr int kTrEpw = 32 / kTrN;  // envs per warp
+constexpr int kTrG = 4, kTrA = kTrN / kTrG;  // lanes per env, agents (and treasures) per lane
+constexpr int kTrEpw = 32 / kTrG;            // envs per warp
 
 template <typename T>
 struct TrLayout {
-  static constexpr int kWarpBytes = (32 * kTrD * (int)sizeof(T) + 127) / 128 * 128;  // 32 rows of 30 values
+  static constexpr int kWarpBytes = (kTrEpw * kTrR * (int)sizeof(T) + 127) / 128 * 128;  // 64 rows of 30 values
   static constexpr int kBlockBytes = kWarpBytes * (kStepThreads / 32);
   static constexpr int kEnvsPerBlock = kTrEpw * (kStepThreads / 32);
 };
@@ -62,25 +67,31 @@ __device__ __forceinline__ T tr_shfl(T v, int src) {
 
 // MODE 0: env.step   1: env.reset (masked / timed-out envs) + observation   2: observation only
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kStepThreads, std::is_same<T, float>::value ? 10 : 1)  // fp32: 48 registers, 40 warps per SM (8: 62 registers, 77.0 us; 10: 76.2; 12: spills, 77.9)
+__global__ void __launch_bounds__(kStepThreads, std::is_same<T, float>::value ? 6 : 1)
     k_treasure(EnvState<T> s, const int32_t *__restrict__ act_u, const uint8_t *__restrict__ mask, int auto_len,
                T *__restrict__ obs, T *__restrict__ rew, uint8_t *__restrict__ done, int32_t *__restrict__ info_i) {
   extern __shared__ __align__(128) unsigned char smem[];
   using TL = TrLayout<T>;
   constexpr bool kF32 = std::is_same<T, float>::value;
+  constexpr int A = kTrA, G = kTrG;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int el = lane >> 3, q = lane & 7, base = el * 8;  // env within the warp, agent, first lane of the env
+  const int el = lane / G, q = lane - el * G, base = el * G;  // env within the warp, lane within the env, its first lane
   const int64_t b0 = ((int64_t)blockIdx.x * (kStepThreads / 32) + warp) * kTrEpw;
   const bool active = b0 + el < s.B;
   const int64_t b = active ? b0 + el : s.B - 1;  // lanes beyond the batch shadow the last env; their stores are predicated off
   const bool full = b0 + kTrEpw <= s.B;
-  const bool coll = q < kTrC;                    // collector (mass 1, size 0.05) or deposit (mass 2.25, size 0.075)
-  const bool has_tr = q < kTrL;                  // this lane also keeps treasure q
+  const bool coll = q < kTrC / A;                // lanes 0..2: collectors (mass 1, size 0.05); lane 3: deposits (2.25, 0.075)
+  const bool has_tr = q < kTrL / A;              // this lane also keeps treasures 2q, 2q + 1
+  const int qt = has_tr ? q : 0;                 // (lane 3 shadows lane 0's treasures: loads stay unpredicated, never stored)
   T *st_obs = reinterpret_cast<T *>(smem + warp * TL::kWarpBytes);
-  T *pv_ptr = s.pv + ((int64_t)q * s.B + b) * 4;
-  T *lm_ptr = s.lm + ((int64_t)(has_tr ? q : 0) * s.B + b) * 2;
+  T *pv_ptr[A], *lm_ptr[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    pv_ptr[k] = s.pv + ((int64_t)(q * A + k) * s.B + b) * 4;
+    lm_ptr[k] = s.lm + ((int64_t)(qt * A + k) * s.B + b) * 2;
+  }
 
-  T px, py, vx, vy, tx = (T)0, ty = (T)0;
+  T px[A], py[A], vx[A], vy[A], tx[A], ty[A];
   uint32_t f;
   uint32_t ep = 0;
   int tstep = 0;
@@ -92,181 +103,216 @@ __global__ void __launch_bounds__(kStepThreads, std::is_same<T, float>::value ? 
     __syncwarp();  // every lane of an env has read the counters before lane 0 of the env rewrites them
     if (doit) {
       // Scenario.reset_world: agents ~ U[-1,1)^2, then per treasure a type and a position ~ 0.95 U[-1,1)^2 (entity e
-      // draws from Philox block e >> 1, components by the parity of e); nobody holds anything
+      // draws from Philox block e >> 1: this lane's two agents are one block, its two treasures another); nobody holds
       ep = ep_old + 1u;
       const uint64_t gid = (uint64_t)(s.gid0 + b);
-      const uint4 ra = philox_raw(s.seed, gid, ep, kDomainReset, q >> 1);
-      px = bits_to_pos<T>((q & 1) ? ra.z : ra.x); py = bits_to_pos<T>((q & 1) ? ra.w : ra.y);
-      vx = vy = (T)0;
-      const uint4 rt = philox_raw(s.seed, gid, ep, kDomainReset, (kTrN + (has_tr ? q : 0)) >> 1);
-      tx = bits_to_pos<T>((q & 1) ? rt.z : rt.x) * (T)0.95; ty = bits_to_pos<T>((q & 1) ? rt.w : rt.y) * (T)0.95;
+      const uint4 ra = philox_raw(s.seed, gid, ep, kDomainReset, q);
+      px[0] = bits_to_pos<T>(ra.x); py[0] = bits_to_pos<T>(ra.y); px[1] = bits_to_pos<T>(ra.z); py[1] = bits_to_pos<T>(ra.w);
+      const uint4 rt = philox_raw(s.seed, gid, ep, kDomainReset, kTrN / 2 + qt);
+      tx[0] = bits_to_pos<T>(rt.x) * (T)0.95; ty[0] = bits_to_pos<T>(rt.y) * (T)0.95;
+      tx[1] = bits_to_pos<T>(rt.z) * (T)0.95; ty[1] = bits_to_pos<T>(rt.w) * (T)0.95;
       const uint4 t0 = philox_raw(s.seed, gid, ep, kDomainGoal, 0), t1 = philox_raw(s.seed, gid, ep, kDomainGoal, 1);
       f = (t0.x >> 31) | ((t0.y >> 31) << 1) | ((t0.z >> 31) << 2) | ((t0.w >> 31) << 3) | ((t1.x >> 31) << 4) |
           ((t1.y >> 31) << 5) | (0x3Fu << 6);
-      if (active) {
-        st4(pv_ptr, Vec4<T>{px, py, vx, vy});
-        if (has_tr) st2(lm_ptr, Vec2<T>{tx, ty});
-        if (q == 0) {
-          if (s.track && t_old > 0) { ret = (double)s.ep_ret[b]; n_ep = 1.0; n_steps = (double)t_old; }
-          s.goal[b] = (int32_t)f;
-          s.episode[b] = ep;
-          s.tstep[b] = 0;
-          s.ep_ret[b] = (T)0;
+#pragma unroll
+      for (int k = 0; k < A; ++k) {
+        vx[k] = vy[k] = (T)0;
+        if (active) {
+          st4(pv_ptr[k], Vec4<T>{px[k], py[k], vx[k], vy[k]});
+          if (has_tr) st2(lm_ptr[k], Vec2<T>{tx[k], ty[k]});
         }
       }
+      if (active && q == 0) {
+        if (s.track && t_old > 0) { ret = (double)s.ep_ret[b]; n_ep = 1.0; n_steps = (double)t_old; }
+        s.goal[b] = (int32_t)f;
+        s.episode[b] = ep;
+        s.tstep[b] = 0;
+        s.ep_ret[b] = (T)0;
+      }
     } else {
-      const Vec4<T> v = ld4(pv_ptr);
-      px = v.x; py = v.y; vx = v.z; vy = v.w;
-      if (has_tr) { const Vec2<T> t = ld2(lm_ptr); tx = t.x; ty = t.y; }
+#pragma unroll
+      for (int k = 0; k < A; ++k) {
+        const Vec4<T> v = ld4(pv_ptr[k]);
+        const Vec2<T> t = ld2(lm_ptr[k]);
+        px[k] = v.x; py[k] = v.y; vx[k] = v.z; vy[k] = v.w; tx[k] = t.x; ty[k] = t.y;
+      }
       f = (uint32_t)s.goal[b];
     }
     if (s.track) fold_stats(s.stats, ret, n_ep, n_steps);
     if (obs == nullptr) return;
   } else {
-    const Vec4<T> v = ld4(pv_ptr);
-    const Vec2<T> t = ld2(lm_ptr);  // lanes 6, 7 read treasure 0 (unused): an unpredicated load is issued up front
-    px = v.x; py = v.y; vx = v.z; vy = v.w;
-    tx = t.x; ty = t.y;
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+      const Vec4<T> v = ld4(pv_ptr[k]);
+      const Vec2<T> t = ld2(lm_ptr[k]);
+      px[k] = v.x; py[k] = v.y; vx[k] = v.z; vy[k] = v.w; tx[k] = t.x; ty[k] = t.y;
+    }
     f = (uint32_t)s.goal[b];
   }
 
+  const T size = coll ? (T)0.05 : (T)0.075;
   if (MODE == 0) {
     // ---- _set_action (one-hot branch, sensitivity = accel) + World.step up to integrate_state ----
-    const int a = act_u[b * kTrN + q];
+    int a[A];
+#pragma unroll
+    for (int k = 0; k < A; ++k) a[k] = act_u[b * kTrN + q * A + k];
     ep = s.episode[b];
     tstep = s.tstep[b];
     const bool has_accel = s.accel >= (T)0;
     const T sens = has_accel ? s.accel : (T)5.0;
-    const T mass = coll ? (T)1.0 : (T)2.25, size = coll ? (T)0.05 : (T)0.075;
-    const T u0 = ((T)0 + ((a == 1 ? (T)1 : (T)0) - (a == 2 ? (T)1 : (T)0))) * sens;
-    const T u1 = ((T)0 + ((a == 3 ? (T)1 : (T)0) - (a == 4 ? (T)1 : (T)0))) * sens;
-    const T k = has_accel ? mass * s.accel : mass;  // apply_action_force: (mass * accel) * action.u
-    T fx = k * u0, fy = k * u1;
-    if constexpr (kF32) {
-      // fp32: every pair ONCE.  The 28 pairs of 8 agents are the 7 xor-rounds q <-> q ^ r; rounds are taken two at a
-      // time, (1,3), (2,6), (4,5): with m = lowest bit of the first round, a lane whose bit m is clear evaluates its
-      // pair of the first round, a lane whose bit m is set its pair of the second (the second round flips bit m, so
-      // exactly one end of every pair qualifies), and each lane receives the force of the one pair it did not
-      // evaluate from the lane that did.  Round 7 is evaluated from both ends.  4 contact evaluations per lane instead
-      // of 8; the accumulation order differs from upstream's (fp32 tolerance), the fp64 build below keeps it.
-      constexpr int kR1[4] = {1, 2, 4, 7}, kR2[4] = {3, 6, 5, 7}, kM[4] = {1, 2, 4, 0};
+    const T mass = coll ? (T)1.0 : (T)2.25;
+    const T kf = has_accel ? mass * s.accel : mass;  // apply_action_force: (mass * accel) * action.u
+    T fx[A], fy[A];
 #pragma unroll
-      for (int sr = 0; sr < 4; ++sr) {
-        const bool low = (q & kM[sr]) == 0;
-        const int p = q ^ (low ? kR1[sr] : kR2[sr]);
-        const T ppx = tr_shfl(px, base + p), ppy = tr_shfl(py, base + p);
-        const bool pc = p < kTrC;
-        const T dx = px - ppx, dy = py - ppy;
+    for (int k = 0; k < A; ++k) {
+      const T u0 = ((T)0 + ((a[k] == 1 ? (T)1 : (T)0) - (a[k] == 2 ? (T)1 : (T)0))) * sens;
+      const T u1 = ((T)0 + ((a[k] == 3 ? (T)1 : (T)0) - (a[k] == 4 ? (T)1 : (T)0))) * sens;
+      fx[k] = kf * u0;
+      fy[k] = kf * u1;
+    }
+    // force_ratio seen from this lane's side against a lane of role `oc`: r = m_other / m_own for the lower index,
+    // 1 / (m_own / m_other) for the higher one - the same number either way: 2.25 (collector against deposit), 1 / 2.25
+    auto ratio = [&](bool oc) { return (coll == oc) ? (T)1 : (coll ? (T)2.25 : (T)(1.0 / 2.25)); };
+    if constexpr (kF32) {
+      {  // the pair inside the block: once, applied to both agents (same mass: ratio 1)
+        const T dx = px[0] - px[1], dy = py[0] - py[1];
         T gx, gy;
-        contact_force<T>(dx, dy, sq2<T>(dx, dy), size + (pc ? (T)0.05 : (T)0.075), gx, gy);
-        const T sc = (coll == pc) ? (T)1 : (coll ? (T)2.25 : (T)(1.0 / 2.25));
-        fx = fmaf(sc, gx, fx);
-        fy = fmaf(sc, gy, fy);
-        if (sr < 3) {
-          const int src = q ^ (low ? kR2[sr] : kR1[sr]);  // evaluated the pair {src, q} with delta = p_src - p_q
-          const T hx = tr_shfl(gx, base + src), hy = tr_shfl(gy, base + src);
-          const bool sc_c = src < kTrC;
-          const T s2 = (coll == sc_c) ? (T)1 : (coll ? (T)2.25 : (T)(1.0 / 2.25));
-          fx = fmaf(-s2, hx, fx);
-          fy = fmaf(-s2, hy, fy);
+        contact_force<T>(dx, dy, sq2<T>(dx, dy), size + size, gx, gy);
+        fx[0] += gx; fy[0] += gy;
+        fx[1] -= gx; fy[1] -= gy;
+      }
+#pragma unroll
+      for (int d = 1; 2 * d <= G; ++d) {
+        const int pb = (q + d) & (G - 1), rb = (q - d) & (G - 1);
+        const bool pc = pb < kTrC / A;
+        T ox[A], oy[A], gx[A][A], gy[A][A];
+#pragma unroll
+        for (int m = 0; m < A; ++m) { ox[m] = tr_shfl(px[m], base + pb); oy[m] = tr_shfl(py[m], base + pb); }
+        const T dmin = size + (pc ? (T)0.05 : (T)0.075), sc = ratio(pc);
+#pragma unroll
+        for (int k = 0; k < A; ++k)
+#pragma unroll
+          for (int m = 0; m < A; ++m) {
+            const T dx = px[k] - ox[m], dy = py[k] - oy[m];
+            contact_force<T>(dx, dy, sq2<T>(dx, dy), dmin, gx[k][m], gy[k][m]);
+            fx[k] = fmaf(sc, gx[k][m], fx[k]);
+            fy[k] = fmaf(sc, gy[k][m], fy[k]);
+          }
+        if (2 * d < G) {  // block q - d evaluated its agents k against MY agents m: mine is the negative, my own ratio
+          const T s2 = ratio(rb < kTrC / A);
+#pragma unroll
+          for (int k = 0; k < A; ++k)
+#pragma unroll
+            for (int m = 0; m < A; ++m) {
+              fx[m] = fmaf(-s2, tr_shfl(gx[k][m], base + rb), fx[m]);
+              fy[m] = fmaf(-s2, tr_shfl(gy[k][m], base + rb), fy[m]);
+            }
         }
       }
     } else {
       T qx[kTrN], qy[kTrN];  // every agent of the env (all shuffles before any predicated code)
 #pragma unroll
-      for (int j = 0; j < kTrN; ++j) { qx[j] = tr_shfl(px, base + j); qy[j] = tr_shfl(py, base + j); }
+      for (int j = 0; j < kTrN; ++j) { qx[j] = tr_shfl(px[j % A], base + j / A); qy[j] = tr_shfl(py[j % A], base + j / A); }
 #pragma unroll
       for (int j = 0; j < kTrN; ++j) {
-        const T pjx = qx[j], pjy = qy[j];
         const bool jc = j < kTrC;
-        const T dist_min = size + (jc ? (T)0.05 : (T)0.075);
-        const T dx = px - pjx, dy = py - pjy;
-        const T d2 = sq2<T>(dx, dy);
-        // force_ratio seen from this lane's side: r = m_other / m_own for the lower index, 1 / (m_own / m_other) for
-        // the higher one - the same number either way: 2.25 (collector against deposit), 1 / 2.25 (the reverse)
-        const T scale = (coll == jc) ? (T)1 : (coll ? (T)2.25 : (T)(1.0 / 2.25));
+        const T dist_min = size + (jc ? (T)0.05 : (T)0.075), scale = ratio(jc);
         const T cut = (coll && jc) ? s.tr_cut[0] : ((coll || jc) ? s.tr_cut[1] : s.tr_cut[2]);
-        if (j != q && !(d2 >= cut)) {  // fp64: upstream's order (other agent's index ascending), far pairs skipped
-          T gx, gy;
-          contact_force<T>(dx, dy, d2, dist_min, gx, gy);
-          fx = scale * gx + fx;
-          fy = scale * gy + fy;
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          const T dx = px[k] - qx[j], dy = py[k] - qy[j];
+          const T d2 = sq2<T>(dx, dy);
+          if (j != q * A + k && !(d2 >= cut)) {  // upstream's order (other agent's index ascending), far pairs skipped
+            T gx, gy;
+            contact_force<T>(dx, dy, d2, dist_min, gx, gy);
+            fx[k] = scale * gx + fx[k];
+            fy[k] = scale * gy + fy[k];
+          }
         }
       }
     }
-    if constexpr (kF32) {
-      // v = 0.75 v + (f / m) dt; the max_speed clip scales by max_speed * rsqrt(|v|^2) (MUFU) instead of an IEEE division
-      const float im = coll ? 0.1f : (float)(0.1 / 2.25);
-      float vxi = fmaf(fx, im, vx * 0.75f), vyi = fmaf(fy, im, vy * 0.75f);
-      if (s.max_speed >= 0.0f) {
-        const float s2 = fmaf(vxi, vxi, vyi * vyi);
-        float rs;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s2));
-        const float sc = s2 > s.max_speed * s.max_speed ? s.max_speed * rs : 1.0f;
-        vxi *= sc; vyi *= sc;
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+      if constexpr (kF32) {
+        // v = 0.75 v + (f / m) dt; the max_speed clip scales by max_speed * rsqrt(|v|^2) (MUFU) instead of an IEEE division
+        const float im = coll ? 0.1f : (float)(0.1 / 2.25);
+        float vxi = fmaf(fx[k], im, vx[k] * 0.75f), vyi = fmaf(fy[k], im, vy[k] * 0.75f);
+        if (s.max_speed >= 0.0f) {
+          const float s2 = fmaf(vxi, vxi, vyi * vyi);
+          float rs;
+          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s2));
+          const float sc = s2 > s.max_speed * s.max_speed ? s.max_speed * rs : 1.0f;
+          vxi *= sc; vyi *= sc;
+        }
+        vx[k] = vxi; vy[k] = vyi;
+        px[k] = fmaf(vxi, 0.1f, px[k]);
+        py[k] = fmaf(vyi, 0.1f, py[k]);
+      } else {
+        integrate_agent<T>(px[k], py[k], vx[k], vy[k], coll ? fx[k] : fx[k] / (T)2.25, coll ? fy[k] : fy[k] / (T)2.25, s.max_speed);
       }
-      vx = vxi; vy = vyi;
-      px = fmaf(vxi, 0.1f, px);
-      py = fmaf(vyi, 0.1f, py);
-    } else {
-      integrate_agent<T>(px, py, vx, vy, coll ? fx : fx / (T)2.25, coll ? fy : fy / (T)2.25, s.max_speed);
+      if (active) st4(pv_ptr[k], Vec4<T>{px[k], py[k], vx[k], vy[k]});
     }
-    if (active) st4(pv_ptr, Vec4<T>{px, py, vx, vy});
   }
 
-  // ---- observation row of agent q (experiments/scenarios.py:95-121) ----
-  const int hold_own = coll ? (int)((f >> (12 + 2 * q)) & 3u) - 1 : -1;
-  uint32_t ct = 0u;  // bit l: this agent touches treasure l (collector radius; only read on collector lanes)
-  T near_key;        // distance (fp64 build) or squared distance (fp32) to the nearest treasure
+  // ---- observation rows of the lane's agents (experiments/scenarios.py:95-121) ----
+  int hold_own[A];
+  uint32_t ct[A];  // bit l: agent k touches treasure l (collector radius; only read on collector lanes)
+  T near_key[A];   // distance (fp64 build) or squared distance (fp32) to the nearest treasure
   {
-    T key[kTrL], dxl[kTrL], dyl[kTrL];
-    int rank[kTrL];
+    T txa[kTrL], tya[kTrL];
 #pragma unroll
-    for (int l = 0; l < kTrL; ++l) { dxl[l] = tr_shfl(tx, base + l); dyl[l] = tr_shfl(ty, base + l); }
+    for (int l = 0; l < kTrL; ++l) { txa[l] = tr_shfl(tx[l % A], base + l / A); tya[l] = tr_shfl(ty[l % A], base + l / A); }
 #pragma unroll
-    for (int l = 0; l < kTrL; ++l) {
-      dxl[l] = dxl[l] - px;
-      dyl[l] = dyl[l] - py;
-      const T d2 = sq2<T>(dxl[l], dyl[l]);
-      key[l] = kF32 ? d2 : sqrt(d2);  // sorted(zip(cached_dist_mag, index)): ties by index
-      rank[l] = l;
-      const bool hit = kF32 ? key[l] < s.tr_t2[2] : key[l] < (T)(0.05 + 0.025);
-      ct |= hit ? (1u << l) : 0u;
-    }
-    near_key = key[0];
-#pragma unroll
-    for (int l = 1; l < kTrL; ++l) near_key = key[l] < near_key ? key[l] : near_key;
-    // rank[m] = m + #{n > m: key[m] > key[n]} - #{l < m: key[l] > key[m]}
-#pragma unroll
-    for (int l = 0; l < kTrL; ++l)
-#pragma unroll
-      for (int m = l + 1; m < kTrL; ++m) {
-        const int gt = key[l] > key[m] ? 1 : 0;
-        rank[l] += gt;
-        rank[m] -= gt;
-      }
-    if (obs != nullptr) {
-      T *row = st_obs + lane * kTrD;  // 120 B rows: the 8 B stores of a half-warp start in 16 different bank pairs
-      st2(row, Vec2<T>{px, py});
-      st2(row + 2, Vec2<T>{vx, vy});
-      st2(row + 4, Vec2<T>{hold_own == 0 ? (T)1 : (T)0, hold_own == 1 ? (T)1 : (T)0});
+    for (int k = 0; k < A; ++k) {
+      hold_own[k] = coll ? (int)((f >> (12 + 2 * (q * A + k))) & 3u) - 1 : -1;
+      T key[kTrL], dxl[kTrL], dyl[kTrL];
+      int rank[kTrL];
+      ct[k] = 0u;
 #pragma unroll
       for (int l = 0; l < kTrL; ++l) {
-        T *dst = row + 6 + 4 * rank[l];
-        const bool t1 = tr_type(f, l) != 0;
-        st2(dst, Vec2<T>{dxl[l], dyl[l]});
-        st2(dst + 2, Vec2<T>{t1 ? (T)0 : (T)1, t1 ? (T)1 : (T)0});
+        dxl[l] = txa[l] - px[k];
+        dyl[l] = tya[l] - py[k];
+        const T d2 = sq2<T>(dxl[l], dyl[l]);
+        key[l] = kF32 ? d2 : sqrt(d2);  // sorted(zip(cached_dist_mag, index)): ties by index
+        rank[l] = l;
+        const bool hit = kF32 ? key[l] < s.tr_t2[2] : key[l] < (T)(0.05 + 0.025);
+        ct[k] |= hit ? (1u << l) : 0u;
+      }
+      near_key[k] = key[0];
+#pragma unroll
+      for (int l = 1; l < kTrL; ++l) near_key[k] = key[l] < near_key[k] ? key[l] : near_key[k];
+      // rank[m] = m + #{n > m: key[m] > key[n]} - #{l < m: key[l] > key[m]}
+#pragma unroll
+      for (int l = 0; l < kTrL; ++l)
+#pragma unroll
+        for (int m = l + 1; m < kTrL; ++m) {
+          const int gt = key[l] > key[m] ? 1 : 0;
+          rank[l] += gt;
+          rank[m] -= gt;
+        }
+      if (obs != nullptr) {
+        T *row = st_obs + (lane * A + k) * kTrD;  // the env's 8 rows are contiguous: lane q writes rows 2q, 2q + 1
+        st2(row, Vec2<T>{px[k], py[k]});
+        st2(row + 2, Vec2<T>{vx[k], vy[k]});
+        st2(row + 4, Vec2<T>{hold_own[k] == 0 ? (T)1 : (T)0, hold_own[k] == 1 ? (T)1 : (T)0});
+#pragma unroll
+        for (int l = 0; l < kTrL; ++l) {
+          T *dst = row + 6 + 4 * rank[l];
+          const bool t1 = tr_type(f, l) != 0;
+          st2(dst, Vec2<T>{dxl[l], dyl[l]});
+          st2(dst + 2, Vec2<T>{t1 ? (T)0 : (T)1, t1 ? (T)1 : (T)0});
+        }
       }
     }
   }
   bool issued = false;
   if (obs != nullptr) {
     T *dst = obs + b0 * kTrR;
-    if (full && (reinterpret_cast<uintptr_t>(obs) & 15) == 0) {  // the warp's 4 envs: 32 x 30 values, contiguous
+    if (full && (reinterpret_cast<uintptr_t>(obs) & 15) == 0) {  // the warp's 8 envs: 64 x 30 values, contiguous
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        bulk_store(dst, st_obs, 32 * kTrD * sizeof(T));
+        bulk_store(dst, st_obs, kTrEpw * kTrR * sizeof(T));
         bulk_commit();
         issued = true;
       }
@@ -281,71 +327,83 @@ __global__ void __launch_bounds__(kStepThreads, std::is_same<T, float>::value ? 
     return;
   }
 
-  // ---- rewards (taken BEFORE post_step), from the distances of this lane's agent after the step ----
-  // holders of this deposit lane's type among the collectors (bit j), from two ballots of the collectors' own holdings
-  const uint32_t holds0 = (__ballot_sync(0xffffffffu, hold_own == 0) >> base) & 0x3Fu;
-  const uint32_t holds1 = (__ballot_sync(0xffffffffu, hold_own == 1) >> base) & 0x3Fu;
-  const uint32_t holders = q == kTrC ? holds0 : holds1;
-  int ncc = coll ? -1 : 0;            // contacts with OTHER collectors (the loop counts the lane's own d2 = 0 as one)
-  T d2dep0 = (T)0, d2dep1 = (T)0;     // squared distance to deposit 0 / 1
-  T m2hold = (T)3.0e38;               // deposit lanes: squared distance to the nearest collector that holds their type
-  T sx = (T)0, sy = (T)0;             // sum of the offsets of the seven other agents (the own offset is an exact 0)
-  uint32_t cdbits = 0u;               // bit d: in contact with deposit d (collector radius pairing)
+  // ---- rewards (taken BEFORE post_step), from the distances of the lane's agents after the step ----
+  // what every collector holds comes from the shared state word: holders of deposit type d as a 6-bit mask
+  uint32_t holders[2] = {0u, 0u}, free_c = 0u;
+#pragma unroll
+  for (int i = 0; i < kTrC; ++i) {
+    const uint32_t h = (f >> (12 + 2 * i)) & 3u;
+    holders[0] |= (h == 1u) ? (1u << i) : 0u;
+    holders[1] |= (h == 2u) ? (1u << i) : 0u;
+    free_c |= (h == 0u) ? (1u << i) : 0u;
+  }
   T nx[kTrN], ny[kTrN];
 #pragma unroll
-  for (int j = 0; j < kTrN; ++j) { nx[j] = tr_shfl(px, base + j); ny[j] = tr_shfl(py, base + j); }
+  for (int j = 0; j < kTrN; ++j) { nx[j] = tr_shfl(px[j % A], base + j / A); ny[j] = tr_shfl(py[j % A], base + j / A); }
+  T r[A];
+  int bench[A], glob_i = 0;
+  uint32_t cdbits[A];  // bit d: agent k in contact with deposit d (collector radius pairing)
+  T shaped[A];
+  int ncc[A];
 #pragma unroll
-  for (int j = 0; j < kTrN; ++j) {
-    const T ox = nx[j] - px, oy = ny[j] - py;
-    const T d2 = sq2<T>(px - nx[j], py - ny[j]);
-    if (j < kTrC) {
-      ncc += d2 < s.tr_t2[0] ? 1 : 0;
-      const T cand = ((holders >> j) & 1u) ? d2 : (T)3.0e38;
-      m2hold = cand < m2hold ? cand : m2hold;
-    } else {
-      if (j == kTrC) d2dep0 = d2; else d2dep1 = d2;
-      cdbits |= (d2 < s.tr_t2[1]) ? (1u << (j - kTrC)) : 0u;
+  for (int k = 0; k < A; ++k) {
+    ncc[k] = coll ? -1 : 0;            // contacts with OTHER collectors (the loop counts the agent's own d2 = 0 as one)
+    T d2dep0 = (T)0, d2dep1 = (T)0;    // squared distance to deposit 0 / 1
+    T m2hold = (T)3.0e38;              // deposit lane: squared distance to the nearest collector holding type k
+    T sx = (T)0, sy = (T)0;            // sum of the offsets of the seven other agents (the own offset is an exact 0)
+    cdbits[k] = 0u;
+#pragma unroll
+    for (int j = 0; j < kTrN; ++j) {
+      const T ox = nx[j] - px[k], oy = ny[j] - py[k];
+      const T d2 = sq2<T>(px[k] - nx[j], py[k] - ny[j]);
+      if (j < kTrC) {
+        ncc[k] += d2 < s.tr_t2[0] ? 1 : 0;
+        const T cand = ((holders[k] >> j) & 1u) ? d2 : (T)3.0e38;  // deposit lane: agent k IS deposit k
+        m2hold = cand < m2hold ? cand : m2hold;
+      } else {
+        if (j == kTrC) d2dep0 = d2; else d2dep1 = d2;
+        cdbits[k] |= (d2 < s.tr_t2[1]) ? (1u << (j - kTrC)) : 0u;
+      }
+      sx += ox; sy += oy;
     }
-    sx += ox; sy += oy;
+    const bool at_dep = hold_own[k] >= 0 && ((cdbits[k] >> (hold_own[k] > 0 ? 1 : 0)) & 1u);
+    // global reward: 5 per (deposit, matching holder in contact) + 5 per (treasure, free collector in contact)
+    glob_i += coll ? ((hold_own[k] < 0 ? 5 * __popc(ct[k]) : 0) + (at_dep ? 5 : 0)) : 0;
+    if (coll) {
+      // nearest treasure while holding nothing, else the deposit of the held type (sqrt is monotone: min of squares)
+      const T kk = hold_own[k] < 0 ? near_key[k] : (hold_own[k] == 0 ? d2dep0 : d2dep1);
+      shaped[k] = (kF32 || hold_own[k] >= 0) ? tr_sqrt<T>(kk) : kk;  // fp64: near_key already is a distance
+      bench[k] = (at_dep || (hold_own[k] < 0 && ct[k] != 0u)) ? 1 : 0;
+    } else {
+      sx = sx / (T)7; sy = sy / (T)7;
+      shaped[k] = tr_sqrt<T>(holders[k] != 0u ? m2hold : sq2<T>(sx, sy));
+      bench[k] = 0;
+    }
   }
-  const bool any_hold = holders != 0u;
-  const bool at_dep = hold_own >= 0 && ((cdbits >> (hold_own > 0 ? 1 : 0)) & 1u);
-  // global reward: 5 per (deposit, matching holder in contact) + 5 per (treasure, free collector in contact)
-  int glob_i = coll ? ((hold_own < 0 ? 5 * __popc(ct) : 0) + (at_dep ? 5 : 0)) : 0;
-  const unsigned env_mask = 0xFFu << base;  // the 8 lanes of this env
+  const unsigned env_mask = ((1u << G) - 1u) << base;  // the lanes of this env
   glob_i = __reduce_add_sync(env_mask, glob_i);
   const T glob = (T)glob_i;
-  T r;
-  int bench;
-  if (coll) {
-    // nearest treasure while holding nothing, else the deposit of the held type (sqrt is monotone: min of squares)
-    const T kk = hold_own < 0 ? near_key : (hold_own == 0 ? d2dep0 : d2dep1);
-    const T shaped = (kF32 || hold_own >= 0) ? tr_sqrt<T>(kk) : kk;  // fp64: near_key already is a distance
-    T rr = (T)(-5 * ncc);
-    rr -= (T)0.1 * shaped;
-    r = rr + glob;
-    bench = (at_dep || (hold_own < 0 && ct != 0u)) ? 1 : 0;
-  } else {
-    sx = sx / (T)7; sy = sy / (T)7;
-    const T m = tr_sqrt<T>(any_hold ? m2hold : sq2<T>(sx, sy));
-    T rr = (T)0;
-    rr -= (T)0.1 * m;
-    r = rr + glob;
-    bench = 0;
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    T rr = coll ? (T)(-5 * ncc[k]) : (T)0;
+    rr -= (T)0.1 * shaped[k];
+    r[k] = rr + glob;
   }
 
   // ---- Scenario.post_step: pick-up, respawn of the treasures collected one step earlier, deposit ----
-  // Every lane runs the same integer logic on the env's state word.  col[l] = collectors in contact with treasure l
-  // (a ballot per treasure, this env's byte of it); pick-up: the lowest-index free collector of col[l].
+  // Every lane runs the same integer logic on the env's state word; the rare parts sit behind warp-uniform tests.
   uint32_t nf = f, taken_mask = 0u;
-  if (__any_sync(0xffffffffu, coll && hold_own < 0 && ct != 0u)) {  // some free collector touches a treasure: rare
-    uint32_t free_c = (__ballot_sync(0xffffffffu, coll && hold_own < 0) >> base) & 0x3Fu;
-    uint32_t col[kTrL];
+  const bool touching = coll && ((hold_own[0] < 0 && ct[0] != 0u) || (hold_own[1] < 0 && ct[1] != 0u));
+  if (__any_sync(0xffffffffu, touching)) {  // some free collector touches a treasure
+    uint32_t cb[kTrC];  // contact bits of every collector, by shuffle
 #pragma unroll
-    for (int l = 0; l < kTrL; ++l) col[l] = (__ballot_sync(0xffffffffu, (ct >> l) & 1u) >> base) & 0x3Fu;
+    for (int i = 0; i < kTrC; ++i) cb[i] = tr_shfl(ct[i % A], base + i / A);
 #pragma unroll
     for (int l = 0; l < kTrL; ++l) {  // branch-free: the warp stays converged
-      const uint32_t cand = tr_alive(f, l) ? (col[l] & free_c) : 0u;
+      uint32_t col = 0u;
+#pragma unroll
+      for (int i = 0; i < kTrC; ++i) col |= ((cb[i] >> l) & 1u) << i;
+      const uint32_t cand = tr_alive(f, l) ? (col & free_c) : 0u;
       const bool t = cand != 0u;
       const int i = (__ffs((int)cand) - 1) & 7;
       free_c = t ? (free_c & ~(1u << i)) : free_c;
@@ -354,36 +412,51 @@ __global__ void __launch_bounds__(kStepThreads, std::is_same<T, float>::value ? 
     }
   }
   const uint32_t dead = ~(f >> 6) & 0x3Fu;  // collected one step earlier: respawn now (respawn_prob = 1.0: the draw always passes)
-  bool moved = has_tr && ((taken_mask >> q) & 1u);
-  if (moved) { tx = (T)-999; ty = (T)-999; }
+  bool moved[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) {
+    moved[k] = has_tr && ((taken_mask >> (q * A + k)) & 1u);
+    if (moved[k]) { tx[k] = (T)-999; ty[k] = (T)-999; }
+  }
   if (dead != 0u) {  // rare
 #pragma unroll 1
     for (int l = 0; l < kTrL; ++l) {
       if (!((dead >> l) & 1u)) continue;
       const uint4 w = philox_raw(s.seed, (uint64_t)(s.gid0 + b), ep, kDomainRespawn, ((uint32_t)(tstep & 0xFFF) << 4) | (uint32_t)l);
-      if (l == q) {
-        tx = bits_to_pos<T>(w.x) * (T)0.95;
-        ty = bits_to_pos<T>(w.y) * (T)0.95;
-        moved = true;
-      }
+#pragma unroll
+      for (int k = 0; k < A; ++k)
+        if (has_tr && l == q * A + k) {
+          tx[k] = bits_to_pos<T>(w.x) * (T)0.95;
+          ty[k] = bits_to_pos<T>(w.y) * (T)0.95;
+          moved[k] = true;
+        }
       nf = (nf & ~(1u << l)) | ((w.z >> 31) << l) | (1u << (6 + l));
     }
   }
-  {  // deposit: a collector that (now) holds type h and touches deposit h lets go; each collector lane decides for itself
-    const int h = coll ? (int)((nf >> (12 + 2 * q)) & 3u) - 1 : -1;
-    const bool drop = h >= 0 && ((cdbits >> (h > 0 ? 1 : 0)) & 1u);
-    if (__any_sync(0xffffffffu, drop)) nf &= ~__reduce_or_sync(env_mask, drop ? (3u << (12 + 2 * q)) : 0u);
+  {  // deposit: a collector that (now) holds type h and touches deposit h lets go; each lane decides for its own agents
+    uint32_t clear = 0u;
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+      const int i = q * A + k;
+      const int h = coll ? (int)((nf >> (12 + 2 * i)) & 3u) - 1 : -1;
+      clear |= (h >= 0 && ((cdbits[k] >> (h > 0 ? 1 : 0)) & 1u)) ? (3u << (12 + 2 * i)) : 0u;
+    }
+    if (__any_sync(0xffffffffu, clear != 0u)) nf &= ~__reduce_or_sync(env_mask, clear);
   }
   T team = (T)0;
-  if (s.track) {  // team return, added in agent order like the thread-per-env kernels
+  if (s.track) {  // team return, added in agent order like the other kernels
 #pragma unroll
-    for (int j = 0; j < kTrN; ++j) team += tr_shfl(r, base + j);
+    for (int j = 0; j < kTrN; ++j) team += tr_shfl(r[j % A], base + j / A);
   }
   if (active) {
-    if (moved) st2(lm_ptr, Vec2<T>{tx, ty});
-    if (rew != nullptr) rew[b * kTrN + q] = r;
-    if (done != nullptr) done[b * kTrN + q] = 0;  // no done_callback (experiments/scenarios.py:186-190): always False
-    if (info_i != nullptr) info_i[b * (kTrN + 1) + q] = bench;
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+      const int64_t row = b * kTrN + q * A + k;
+      if (moved[k]) st2(lm_ptr[k], Vec2<T>{tx[k], ty[k]});
+      if (rew != nullptr) rew[row] = r[k];
+      if (done != nullptr) done[row] = 0;  // no done_callback (experiments/scenarios.py:186-190): always False
+      if (info_i != nullptr) info_i[b * (kTrN + 1) + q * A + k] = bench[k];
+    }
     if (q == 0) {
       s.goal[b] = (int32_t)nf;
       s.tstep[b] = tstep + 1;
