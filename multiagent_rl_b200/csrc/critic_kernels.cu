@@ -74,7 +74,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-constexpr int kCriticR = 2;  // samples per warp and pass: every weight row read from shared memory serves both
+constexpr int kCriticR = 4;  // samples per warp and pass: every weight row read from shared memory serves all of them
+                             // (1: 1.61 ms, 2: 1.06 ms, 4: 0.90 ms for 65,536 x 3 agent rows; 235 registers, no spills)
 
 // per-warp staging: the input rows, x_t = relu(dense1) and h_{t-1} of the warp's kCriticR samples (every step's output,
 // which the attention needs, stays in the registers of the lane that owns the unit)
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kCriticThreads, 1)
 #pragma unroll
     for (int u = 0; u < kCriticR; ++u) {
       ok[u] = pass * kCriticR + u < B;
-      bs[u] = ok[u] ? pass * kCriticR + u : pass * kCriticR;  // an odd tail recomputes its first sample, stores nothing
+      bs[u] = ok[u] ? pass * kCriticR + u : pass * kCriticR;  // a ragged tail recomputes its first sample, stores nothing
     }
     float c0[kCriticR], c1[kCriticR], h0[kCriticR], h1[kCriticR];
     float o0[kCriticR][kCriticMaxAgents], o1[kCriticR][kCriticMaxAgents];  // outputs of the lane's two units, per step
