@@ -21,6 +21,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+
+def _gpu_spin(torch, cycles=20_000_000):
+    """~10 ms of GPU-side spinning before a timed launch loop, so that the host enqueues ahead of the GPU and the
+    kernels run back to back (torch.cuda._sleep is a private helper: skipped quietly where it does not exist)."""
+    spin = getattr(torch.cuda, '_sleep', None)
+    if spin is not None:
+        spin(cycles)
+
 SCENARIO, N_AGENTS, OBS_DIM, ACT_DIM, EP_LEN = 'simple_spread', 3, 10, 5, 25
 SEED = 12345678  # main.py:41
 # algorithmic bytes of one env step (SURVEY.md 8d): 41N + 8L + 4ND with N = L = 3, D = 10
@@ -303,7 +311,7 @@ def run_b200(args):
     sync_all()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
-    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin (outside every event pair): the host enqueues ahead of the GPU, so no
+    _gpu_spin(torch)  # ~10 ms GPU spin (outside every event pair): the host enqueues ahead of the GPU, so no
     #                                event pair contains a wait for a launch that Python had not issued yet
     for k in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the event pair)
@@ -491,7 +499,7 @@ def side_measurements(m, actor, dev, pk, off):
     torch.cuda.synchronize()
     reps = 48
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
+    _gpu_spin(torch)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
     e0.record()
     for i in range(reps):
         env.step(act, out=rot[i % 4])  # 280 MB of algorithmic traffic per launch, outputs rotate over 566 MB
@@ -515,7 +523,7 @@ def side_measurements(m, actor, dev, pk, off):
     for _ in range(2):
         actor.forward(obs[:262144])
     torch.cuda.synchronize()
-    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
+    _gpu_spin(torch)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
     e0.record()
     for _ in range(5):
         actor.forward(obs[:262144])
@@ -538,7 +546,7 @@ def side_measurements(m, actor, dev, pk, off):
     for t in range(3):
         fused(t)
     torch.cuda.synchronize()
-    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
+    _gpu_spin(torch)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
     e0.record()
     for t in range(20):
         fused(3 + t)
@@ -569,7 +577,7 @@ def side_measurements(m, actor, dev, pk, off):
         fused_shard(i % nsh, i // nsh)
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10 * nsh)]
-    torch.cuda._sleep(20_000_000)
+    _gpu_spin(torch)
     for i, (a, b) in enumerate(evs):
         a.record()
         fused_shard(i % nsh, 2 + i // nsh)

@@ -9,6 +9,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiagent_rl_b200 as m  # noqa: E402
 
 
+
+def _gpu_spin(torch, cycles=20_000_000):
+    """~10 ms of GPU-side spinning before a timed launch loop, so that the host enqueues ahead of the GPU and the
+    kernels run back to back (torch.cuda._sleep is a private helper: skipped quietly where it does not exist)."""
+    spin = getattr(torch.cuda, '_sleep', None)
+    if spin is not None:
+        spin(cycles)
+
 def run(dev, peak, verbose=False):
     N, D, A = 3, 10, 5
     B, cap, batch = 1 << 20, 1 << 22, 1 << 20
@@ -21,7 +29,7 @@ def run(dev, peak, verbose=False):
             fn()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches are all queued before the first one starts
+        _gpu_spin(torch)  # ~10 ms GPU spin: the timed launches are all queued before the first one starts
         e0.record()
         for _ in range(reps):
             fn()

@@ -9,6 +9,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multiagent_rl_b200 as m  # noqa: E402
 from multiagent_rl_b200.networks import random_state_dict  # noqa: E402
 
+
+def _gpu_spin(torch, cycles=20_000_000):
+    """~10 ms of GPU-side spinning before a timed launch loop, so that the host enqueues ahead of the GPU and the
+    kernels run back to back (torch.cuda._sleep is a private helper: skipped quietly where it does not exist)."""
+    spin = getattr(torch.cuda, '_sleep', None)
+    if spin is not None:
+        spin(cycles)
+
 CONFIGS = [('simple_spread', None, 65536), ('simple_spread', 6, 65536), ('simple_spread', 9, 32768),
            ('simple_spread', 12, 32768), ('simple_reference', None, 65536), ('simple_speaker_listener', None, 65536),
            ('fullobs_collect_treasure', None, 32768)]
@@ -24,7 +32,7 @@ for scen, n, B in CONFIGS:
     env.rollout(actor, T)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda._sleep(20_000_000)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
+    _gpu_spin(torch)  # ~10 ms GPU spin: the timed launches below are all queued before the first one starts
     e0.record()
     for _ in range(4):
         env.rollout(actor, T)
